@@ -1,0 +1,330 @@
+"""Host side above the C-ABI: gene table, name interning, plan/emit orchestration, drains.
+
+What the reference does per sample in Python (minimizer_2.py:20-101) is done here once
+per batch: the record is reduced to a gene table + bytes and uploaded (`gm2_set_reference`),
+gene names are interned to ids (`gm2_set_name_map`), every sample's list becomes a row of
+ids (`gm2_load_ids_host`), and the device produces lengths, record offsets and the FASTA
+image (`gm2_plan`, `gm2_emit_*`).  All compute is in libgm2.so; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from .genbank import sequence_bytes
+
+DEFAULT_CHUNK_BYTES = int(os.environ.get("GM2_CHUNK_BYTES", 256 << 20))
+SEQ_ID_PREFIX = "Minimized_E_coli_K12_MG1655_"      # the reference's literal (minimizer_2.py:476, :537)
+
+
+class GeneTable:
+    """`gene` features of a record in file order (minimizer_2.py:59-61, :78-79) + name interning."""
+
+    def __init__(self, names: Sequence[str], starts: np.ndarray, ends: np.ndarray, features: Optional[list] = None):
+        self.names = list(names)
+        self.starts = np.asarray(starts, dtype=np.int64)
+        self.ends = np.asarray(ends, dtype=np.int64)
+        self.features = features            # the record's gene feature objects (for GenomeMinimiser.features)
+        # intern: id = order of first appearance; CSR id -> gene indices (1:many for duplicate names)
+        self.name_to_id: Dict[str, int] = {}
+        buckets: List[List[int]] = []
+        for g, nm in enumerate(self.names):
+            i = self.name_to_id.get(nm)
+            if i is None:
+                i = len(buckets)
+                self.name_to_id[nm] = i
+                buckets.append([])
+            buckets[i].append(g)
+        self.id2gene_off = np.zeros(len(buckets) + 1, dtype=np.int32)
+        if buckets:
+            self.id2gene_off[1:] = np.cumsum([len(b) for b in buckets])
+        self.id2gene_idx = np.asarray([g for b in buckets for g in b], dtype=np.int32)
+
+    @property
+    def F(self) -> int:
+        return len(self.names)
+
+    @property
+    def V(self) -> int:
+        return len(self.name_to_id)
+
+    @classmethod
+    def from_record(cls, record) -> "GeneTable":
+        names, starts, ends, feats = [], [], [], []
+        for feat in record.features:
+            if feat.type == "gene":
+                names.append(feat.qualifiers.get("gene", [""])[0])
+                # AttributeError on a None location, as in the reference (minimizer_2.py:78)
+                starts.append(int(feat.location.start))
+                ends.append(int(feat.location.end))
+                feats.append(feat)
+        return cls(names, np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64), feats)
+
+    def ids_for(self, needed) -> List[int]:
+        """Ids of the table's names that satisfy Python's `name in needed` (minimizer_2.py:62)."""
+        if isinstance(needed, np.ndarray):
+            needed = needed.tolist()
+        if isinstance(needed, (str, bytes)):
+            # a bare string: `in` is a substring test — reproduce it rather than "fix" it
+            if isinstance(needed, bytes):
+                return []
+            return [i for nm, i in self.name_to_id.items() if nm in needed]
+        get = self.name_to_id.get
+        out = []
+        for x in needed:
+            try:
+                i = get(x)
+            except TypeError:              # unhashable element: never equal to a str
+                continue
+            if i is not None:
+                out.append(i)
+        return out
+
+    def tokenize(self, all_lists: Iterable) -> Tuple[np.ndarray, np.ndarray]:
+        """Gene-name lists -> CSR (ids int32, off int64).  Names that match no gene are dropped
+        here (they cannot influence the result); duplicates are kept (idempotent on the device)."""
+        rows = [self.ids_for(needed) for needed in all_lists]
+        off = np.zeros(len(rows) + 1, dtype=np.int64)
+        if rows:
+            off[1:] = np.cumsum([len(r) for r in rows])
+        ids = np.fromiter((i for r in rows for i in r), dtype=np.int32, count=int(off[-1]))
+        return ids, off
+
+    def keep_rows_from_bool(self, keep: np.ndarray) -> np.ndarray:
+        """Boolean [S, F] -> packed little-endian uint32 rows [S, ceil(F/32)]."""
+        keep = np.atleast_2d(np.asarray(keep, dtype=bool))
+        S, F = keep.shape
+        fw = (F + 31) // 32
+        padded = np.zeros((S, fw * 32), dtype=np.uint8)
+        padded[:, :F] = keep
+        return np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(S, fw)
+
+
+def default_device() -> int:
+    for key in ("GM2_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(key)
+        if v is not None and v != "":
+            return int(v)
+    return 0
+
+
+class MinimizerEngine:
+    """One reference genome resident on one GPU; plans and emits batches of samples."""
+
+    def __init__(self, record=None, *, seq: Optional[np.ndarray] = None, table: Optional[GeneTable] = None,
+                 device: Optional[int] = None, config: Optional[Dict[int, int]] = None):
+        if record is not None:
+            seq = sequence_bytes(record)
+            table = GeneTable.from_record(record)
+        if seq is None or table is None:
+            raise ValueError("MinimizerEngine needs a record, or seq + table")
+        self.seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        self.table = table
+        self.G = int(self.seq.size)
+        self.device = default_device() if device is None else int(device)
+        self.ctx = _native.Context(self.device)            # raises if CUDA is unusable: no fallback
+        for k, v in (config or {}).items():
+            self.ctx.configure(k, v)
+        self.ctx.set_reference(self.seq, table.starts, table.ends)
+        self.ctx.set_name_map(table.id2gene_off, table.id2gene_idx)
+        self.first_idx = 0
+        self._pinned: List[Optional[_native.PinnedBuffer]] = [None, None]
+
+    def close(self):
+        for b in self._pinned:
+            if b is not None:
+                b.free()
+        self._pinned = [None, None]
+        self.ctx.close()
+
+    # -- planning ---------------------------------------------------------------------------
+    def plan_lists(self, all_lists: Iterable, first_idx: int = 0) -> np.ndarray:
+        ids, off = self.table.tokenize(all_lists)
+        return self.plan_ids(ids, off, first_idx)
+
+    def plan_ids(self, ids: np.ndarray, off: np.ndarray, first_idx: int = 0) -> np.ndarray:
+        self.ctx.load_ids_host(ids, off)
+        self.ctx.plan(first_idx)
+        self.first_idx = first_idx
+        return self.ctx.lengths()
+
+    def plan_keep_rows(self, rows: np.ndarray, first_idx: int = 0) -> np.ndarray:
+        self.ctx.load_keep_host(rows)
+        self.ctx.plan(first_idx)
+        self.first_idx = first_idx
+        return self.ctx.lengths()
+
+    @property
+    def S(self) -> int:
+        return self.ctx.S
+
+    # -- results ------------------------------------------------------------------------------
+    def image(self, s0: int = 0, s1: Optional[int] = None) -> np.ndarray:
+        """Concatenated FASTA records [s0,s1) as one uint8 array (host)."""
+        s1 = self.S if s1 is None else s1
+        n = self.ctx.image_bytes(s0, s1)
+        out = np.empty(n, dtype=np.uint8)
+        self.ctx.emit_host(s0, s1, out)
+        return out
+
+    def sequence(self, s: int) -> str:
+        """Minimized sequence of sample s as str (what GenomeMinimiser.reduced_genome_str holds)."""
+        off = self.ctx.record_offsets()
+        L = int(self.ctx.lengths()[s])
+        img = self.image(s, s + 1)
+        hdr = int(off[s + 1] - off[s]) - L - 1
+        return img[hdr:hdr + L].tobytes().decode("ascii")
+
+    def minimize_one(self, needed, idx: int = 0) -> Tuple[np.ndarray, str]:
+        """One sample: (indices of the REMOVED genes in file order, minimized sequence)."""
+        self.plan_lists([needed], first_idx=idx)
+        row = self.ctx.keep_rows()[0]
+        kept = np.unpackbits(row.view(np.uint8), bitorder="little")[:self.table.F].astype(bool)
+        return np.flatnonzero(~kept), self.sequence(0)
+
+    def _pin(self, i: int, nbytes: int) -> _native.PinnedBuffer:
+        b = self._pinned[i]
+        if b is None or b.nbytes < nbytes:
+            if b is not None:
+                b.free()
+            b = _native.PinnedBuffer(nbytes)
+            self._pinned[i] = b
+        return b
+
+    def chunks(self, max_bytes: int = DEFAULT_CHUNK_BYTES, s0: int = 0, s1: Optional[int] = None
+               ) -> List[Tuple[int, int]]:
+        """Split [s0,s1) into contiguous sample ranges of at most max_bytes of image each
+        (a single record larger than max_bytes gets a range of its own)."""
+        s1 = self.S if s1 is None else s1
+        off = self.ctx.record_offsets()
+        out = []
+        a = s0
+        while a < s1:
+            b = int(np.searchsorted(off, off[a] + max_bytes, side="right")) - 1
+            b = min(max(b, a + 1), s1)
+            out.append((a, b))
+            a = b
+        return out
+
+    def drain(self, sink: Callable[[int, int, np.ndarray], None], max_bytes: int = 0,
+              s0: int = 0, s1: Optional[int] = None) -> int:
+        """Produce records [s0,s1) chunk by chunk into two pinned buffers and hand each chunk to
+        `sink(sa, sb, bytes_view)`; the GPU fills one buffer while the sink consumes the other.
+        Returns the total number of bytes delivered."""
+        ranges = self.chunks(max_bytes or DEFAULT_CHUNK_BYTES, s0, s1)
+        if not ranges:
+            return 0
+        off = self.ctx.record_offsets()
+        need = max(int(off[b] - off[a]) for a, b in ranges)
+        bufs = [self._pin(0, need), self._pin(1, need)]
+        total = 0
+        err: List[BaseException] = []
+
+        def produce(i: int):
+            try:
+                a, b = ranges[i]
+                self.ctx.emit_host(a, b, bufs[i & 1])
+            except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
+                err.append(e)
+
+        produce(0)
+        for i, (a, b) in enumerate(ranges):
+            if err:
+                raise err[0]
+            t = None
+            if i + 1 < len(ranges):
+                t = threading.Thread(target=produce, args=(i + 1,))
+                t.start()                                   # ctypes releases the GIL during the call
+            n = int(off[b] - off[a])
+            sink(a, b, bufs[i & 1].array[:n])
+            total += n
+            if t is not None:
+                t.join()
+        if err:
+            raise err[0]
+        return total
+
+
+def shard_range(S: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous sample range of `rank` (rank order == file order)."""
+    return (rank * S) // world, ((rank + 1) * S) // world
+
+
+# ----------------------------------------------------------------------------------------------
+# batch entry points behind minimizer_2.process_multiple_genomes_* (reference :447-560)
+# ----------------------------------------------------------------------------------------------
+def _pct(original_length: int, genome_length: int) -> float:
+    return (original_length - genome_length) / original_length * 100.0
+
+
+def _sampled(idx: int) -> bool:
+    """The reference reports (and, in single-file mode, accumulates) only these samples (:482, :550)."""
+    return idx <= 9 or (idx + 1) % 100 == 0
+
+
+def run_single_file(record, all_lists, model_name: str, output_file: str, engine: Optional[MinimizerEngine] = None) -> dict:
+    n = len(all_lists)
+    G = len(record.seq)
+    eng = engine or MinimizerEngine(record)
+    try:
+        lengths = eng.plan_lists(all_lists, first_idx=0)
+        with open(output_file, "wb") as out:
+            out.write((f"# Minimized genomes generated using model: {model_name}\n"
+                       f"# Total genomes: {n}\n"
+                       f"# Generated on: {np.datetime64('now')}\n").encode())
+
+            def sink(sa: int, sb: int, view: np.ndarray) -> None:
+                out.write(view)
+                for idx in range(sa, sb):                      # same lines, same order as the reference
+                    print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
+                    if _sampled(idx):
+                        L = int(lengths[idx])
+                        print(f"  → {L:,} bp ({_pct(G, L):.1f}% reduction)")
+
+            eng.drain(sink)
+    finally:
+        if engine is None:
+            eng.close()
+    # F10: only the reported samples are summed, the divisor is still n (float64, same order)
+    tot_red, tot_len = 0.0, 0
+    for idx in range(n):
+        if _sampled(idx):
+            tot_red += _pct(G, int(lengths[idx]))
+            tot_len += int(lengths[idx])
+    return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}
+
+
+def run_multi_file(record, all_lists, model_name: str, output_dir, filename_template: str,
+                   engine: Optional[MinimizerEngine] = None) -> dict:
+    n = len(all_lists)
+    G = len(record.seq)
+    print(f"Writing {n} individual FASTA files to: {output_dir}")
+    eng = engine or MinimizerEngine(record)
+    try:
+        lengths = eng.plan_lists(all_lists, first_idx=0)
+        rec_off = eng.ctx.record_offsets()
+
+        def sink(sa: int, sb: int, view: np.ndarray) -> None:
+            base = int(rec_off[sa])
+            for idx in range(sa, sb):
+                print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
+                fname = filename_template.format(model=model_name, idx=idx)
+                with open(os.path.join(output_dir, fname), "wb") as fh:
+                    fh.write(view[int(rec_off[idx]) - base:int(rec_off[idx + 1]) - base])
+                if _sampled(idx):
+                    L = int(lengths[idx])
+                    print(f"  → saved {fname} | {L:,} bp ({_pct(G, L):.1f}% reduction)")
+
+        eng.drain(sink)
+    finally:
+        if engine is None:
+            eng.close()
+    tot_red, tot_len = 0.0, 0
+    for idx in range(n):
+        tot_red += _pct(G, int(lengths[idx]))
+        tot_len += int(lengths[idx])
+    return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}

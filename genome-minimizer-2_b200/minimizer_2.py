@@ -1,0 +1,129 @@
+"""Drop-in facade for the reference module `src/genome_minimizer_2/minimizer/minimizer_2.py`.
+
+The reference's CLI imports two functions from that module (main.py:554-557) and calls them
+at main.py:582-587 / :599-604.  This module exposes the same names with the same arguments,
+defaults, stdout lines, output files and return values; the per-sample Python loops of the
+reference (minimizer_2.py:50-101) run as one batched job in libgm2.so on a B200.
+
+  GenomeMinimiser                            reference :19-270 (constructor does all the work)
+  process_multiple_genomes_single_file       reference :447-495
+  process_multiple_genomes_multiple_files    reference :499-560
+
+Preserved on purpose: records are never line-wrapped; the single-file
+preamble's third line is `np.datetime64('now')`; single-file averages add up only samples
+with idx<=9 or (idx+1)%100==0 yet divide by N; an empty `.npy` ends in ZeroDivisionError.
+Not provided: the plotting / duplicate-report helpers (reference :212-252, :273-444) — they
+are unreachable from the CLI and outside the hot path.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import engine as _engine
+from .genbank import read_genbank
+
+# default output root, the analogue of utils/directories.py:10 in the reference tree
+PROJECT_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+SEQ_ID_PREFIX = _engine.SEQ_ID_PREFIX
+_GENBANK_SUFFIXES = (".gb", ".genbank", ".gbff")
+
+
+def _default_dir() -> str:
+    return os.path.join(PROJECT_ROOT, "minimized_genomes")
+
+
+class GenomeMinimiser:
+    """One sample's minimization; attribute-compatible with the reference class.
+
+    Attributes after construction: idx, model_name, record, wildtype_sequence,
+    original_genome_length, needed_genes, features (removed gene features, file order),
+    positions_to_remove (set, built on first access), reduced_genome_str.
+    `engine=` is an extension: reuse a genome already resident on the GPU.
+    """
+
+    def __init__(self, record_path: str = None, needed_genes_path: str = None, idx: int = 0,
+                 model_name: str = "", record=None, all_needed_gene_lists: list = None,
+                 needed_genes_list: list = None, engine: Optional[_engine.MinimizerEngine] = None):
+        self.idx, self.model_name = idx, model_name
+        self.record = self.load_genome(record_path) if record is None else record
+        self.wildtype_sequence = self.record
+        self.original_genome_length = len(self.record.seq)
+        # same precedence as reference :38-43
+        if needed_genes_list is not None:
+            self.needed_genes = needed_genes_list
+        elif all_needed_gene_lists is not None:
+            self.needed_genes = all_needed_gene_lists[idx]
+        else:
+            self.needed_genes = self.get_needed_genes(needed_genes_path)[idx]
+
+        eng = engine or _engine.MinimizerEngine(self.record)
+        try:
+            removed, self.reduced_genome_str = eng.minimize_one(self.needed_genes, idx)
+        finally:
+            if engine is None:
+                eng.close()
+        self.features = [eng.table.features[g] for g in removed]                    # reference :50-66
+        self._spans = [(int(eng.table.starts[g]), int(eng.table.ends[g])) for g in removed]
+        self._positions: Optional[set] = None
+
+    @property
+    def positions_to_remove(self) -> set:
+        """Reference :68-83.  About 2 M Python ints for a K-12 genome, so built lazily."""
+        if self._positions is None:
+            self._positions = set()
+            for a, b in self._spans:
+                self._positions.update(range(a, b))
+        return self._positions
+
+    # -- loaders used only when record / lists are not passed in (reference :127-210) ----------
+    def load_genome(self, file_path: str):
+        if not os.path.isfile(file_path):
+            raise FileNotFoundError(f"The file {file_path} does not exist.")
+        if not file_path.endswith(_GENBANK_SUFFIXES):
+            raise ValueError(f"The file {file_path} could not be read.\nEnsure the file holds a GenBank format.")
+        return read_genbank(file_path)
+
+    def get_needed_genes(self, file_path: str) -> list:
+        if not os.path.isfile(file_path):
+            raise FileNotFoundError(f"The file {file_path} does not exist.")
+        if not file_path.endswith(".npy"):
+            raise ValueError(f"Invalid file format. Expected .npy file, got: {os.path.splitext(file_path)[1]}")
+        return np.load(file_path, allow_pickle=True).tolist()
+
+    # -- small helpers (reference :103-125, :254-270) ----------------------------------------------
+    def save_minimized_genome(self, file_path: str):
+        os.makedirs(_default_dir(), exist_ok=True)
+        with open(file_path, "w") as fh:            # header line + sequence, no trailing newline
+            fh.write(f">{SEQ_ID_PREFIX}{self.idx+1}\n{self.reduced_genome_str}")
+
+    def get_reduction_stats(self) -> dict:
+        n0, n1 = self.original_genome_length, len(self.reduced_genome_str)
+        return {"original_length": n0, "reduced_length": n1,
+                "reduction_percentage": (n0 - n1) / n0 * 100,
+                "genes_removed": len(self.features),
+                "positions_removed": len(self.positions_to_remove)}
+
+
+def process_multiple_genomes_single_file(genome_path: str, genes_path: str, model_name: str, output_file: str = None):
+    """All samples into ONE FASTA file; returns {"genome_count", "average_reduction_pct", "average_length_bp"}."""
+    if not output_file:
+        output_file = os.path.join(_default_dir(), f"minimized_genomes_{model_name}.fasta")
+    os.makedirs(os.path.dirname(output_file), exist_ok=True)
+    record = read_genbank(os.fspath(genome_path))                      # reference :455
+    all_lists = np.load(genes_path, allow_pickle=True).tolist()        # reference :456
+    return _engine.run_single_file(record, all_lists, model_name, output_file)
+
+
+def process_multiple_genomes_multiple_files(genome_path: str, genes_path: str, model_name: str,
+                                            output_dir: str = None,
+                                            filename_template: str = "minimized_{model}_{idx:04d}.fasta"):
+    """Each sample into its own FASTA file under output_dir; same return dict (all samples averaged)."""
+    if output_dir is None:
+        output_dir = _default_dir()
+    os.makedirs(output_dir, exist_ok=True)
+    record = read_genbank(os.fspath(genome_path))                      # reference :515
+    all_lists = np.load(genes_path, allow_pickle=True).tolist()        # reference :518
+    return _engine.run_multi_file(record, all_lists, model_name, output_dir, filename_template)

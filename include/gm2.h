@@ -1,0 +1,169 @@
+/* gm2.h — C-ABI of libgm2.so, the B200 (sm_100a) build of genome-minimizer-2's
+ * `--mode minimizer` hot path.
+ *
+ * The reference (ucl-cssb/genome-minimizer-2) is pure Python and has NO native
+ * interface of its own: the path is the constructor of
+ * `GenomeMinimiser` (src/genome_minimizer_2/minimizer/minimizer_2.py:20-101) and the
+ * two batch entry functions around it (:447-495, :499-560).  This header is the
+ * boundary a maintainer would bind from those functions with ctypes; each entry
+ * point cites the reference lines whose work it takes over.  INTEGRATION.md shows
+ * the binding.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch types: pointers + sizes only.
+ *   - every function returns GM2_OK (0) or a negative GM2_ERR_* code; the text of
+ *     the last failure on a context is `gm2_last_error(ctx)`.
+ *   - "host" pointers are ordinary (pageable or pinned) CPU memory owned by the
+ *     caller and only read/written during the call.  "dev" pointers are CUDA device
+ *     pointers on the context's device (e.g. `torch.Tensor.data_ptr()`).
+ *   - one context per GPU; a context is not thread-safe, distinct contexts are
+ *     independent.  All device work of a context is issued on its stream
+ *     (`gm2_set_stream`), and calls that return host data synchronise that stream.
+ *   - there is no CPU fallback: without a usable CUDA device `gm2_create` fails.
+ *
+ * Data model
+ *   reference  : G upper-case ASCII bases + F `gene` intervals [start,end) in file order
+ *   sample s   : a keep vector over the F genes (bit g set  <=>  name_g in the sample's list)
+ *   output     : for s ascending   ">" prefix (first_idx+s+1) "\n"  kept bases  "\n"
+ *                a base p is deleted iff some NOT-kept gene has start <= p < end.
+ */
+#ifndef GM2_H_
+#define GM2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM2_ABI_VERSION 1
+
+#define GM2_OK            0
+#define GM2_ERR_INVALID  -1   /* bad argument                                  */
+#define GM2_ERR_CUDA     -2   /* a CUDA runtime call or kernel launch failed   */
+#define GM2_ERR_STATE    -3   /* call made in the wrong order                  */
+#define GM2_ERR_CAPACITY -4   /* caller's output buffer is too small           */
+#define GM2_ERR_NOMEM    -5   /* host or device allocation failed              */
+
+/* gm2_configure keys */
+#define GM2_CFG_TILE_BYTES    1  /* reference bases staged per CTA (multiple of 4096; before set_reference) */
+#define GM2_CFG_EMIT_WARPS    2  /* warps per emit CTA (1..32)                               */
+#define GM2_CFG_EMIT_BATCH    3  /* samples per emit CTA; 0 = choose from S and the SM count */
+#define GM2_CFG_PACKING       4  /* 0 auto, 1 byte/base, 2 two-bit (ACGT-only references)    */
+#define GM2_CFG_STORE_POLICY  5  /* 0 default stores, 1 streaming (st.global.cs)             */
+
+/* gm2_query keys */
+#define GM2_Q_SM_COUNT        1
+#define GM2_Q_LAUNCHES        2  /* kernels launched by this context so far */
+#define GM2_Q_NUM_SEGMENTS    3  /* elementary segments between breakpoints */
+#define GM2_Q_NUM_TILES       4
+#define GM2_Q_PACKING         5  /* packing actually in use (1 or 2)        */
+#define GM2_Q_NUM_SLOTS       6
+#define GM2_Q_KEEP_WORDS      7  /* 32-bit words per keep row = ceil(F/32)  */
+
+typedef struct gm2_ctx gm2_ctx;
+
+int         gm2_abi_version(void);
+/* Number of CUDA devices visible, or a negative error. */
+int         gm2_device_count(void);
+
+/* Lifetime.  `device` is a CUDA ordinal.  Fails (no fallback) if CUDA is unusable. */
+int         gm2_create(int device, gm2_ctx** out);
+int         gm2_destroy(gm2_ctx* ctx);
+const char* gm2_last_error(const gm2_ctx* ctx);      /* ctx may be NULL: create-time error */
+int         gm2_configure(gm2_ctx* ctx, int key, int64_t value);
+int         gm2_query(const gm2_ctx* ctx, int key, int64_t* out);
+/* Issue this context's work on the caller's CUDA stream (cudaStream_t passed as
+ * void*; NULL restores the context's own stream). */
+int         gm2_set_stream(gm2_ctx* ctx, void* cuda_stream);
+int         gm2_sync(gm2_ctx* ctx);
+
+/* The record:  replaces `record.seq` (minimizer_2.py:35, :94) and, for every feature
+ * with type == "gene" in file order, `int(feature.location.start)` /
+ * `int(feature.location.end)` (minimizer_2.py:59-60, :78-79).  `seq` is G upper-case
+ * ASCII bytes (any letter).  Intervals are clamped to [0,G]; start >= end deletes
+ * nothing (Python `range` semantics).  Builds the static segment tables on the host
+ * and uploads everything; host pointers are not retained. */
+int gm2_set_reference(gm2_ctx* ctx, const uint8_t* seq, int64_t G,
+                      const int64_t* gene_start, const int64_t* gene_end, int32_t F);
+
+/* Name table:  replaces `feature.qualifiers.get("gene", [""])[0]` + `name not in
+ * needed_genes` (minimizer_2.py:61-62) after the host has interned names to ids
+ * 0..V-1.  CSR id -> gene indices (1:many: several genes may share a name). */
+int gm2_set_name_map(gm2_ctx* ctx, const int32_t* id2gene_off /* V+1 */,
+                     const int32_t* id2gene_idx, int32_t V);
+
+/* Record header: '>' + prefix + decimal(first_idx+s+1) + '\n'.  Default prefix is the
+ * reference's literal "Minimized_E_coli_K12_MG1655_" (minimizer_2.py:476, :537). */
+int gm2_set_header_prefix(gm2_ctx* ctx, const char* prefix);
+
+/* Samples in: either interned name-id lists (CSR; ids outside 0..V-1 and duplicates
+ * are legal and ignored/idempotent) or ready keep rows of ceil(F/32) little-endian
+ * 32-bit words each.  *_host copy from CPU memory into context-owned device buffers;
+ * *_dev borrow device memory in place (zero copy): the caller keeps ownership and
+ * must keep it alive and unchanged until the next gm2_load_* or gm2_destroy. */
+int gm2_load_ids_host(gm2_ctx* ctx, const int32_t* ids, const int64_t* off /* S+1 */, int64_t S);
+int gm2_load_ids_dev (gm2_ctx* ctx, const int32_t* ids, const int64_t* off /* S+1 */, int64_t S, int64_t n_ids);
+int gm2_load_keep_host(gm2_ctx* ctx, const uint32_t* keep_rows, int64_t S);
+int gm2_load_keep_dev (gm2_ctx* ctx, const uint32_t* keep_rows, int64_t S);
+
+/* K1 keep-mask builder (ids mode only), K2 segment flags, K3 scans: replaces
+ * `_extract_non_essential_genes` (minimizer_2.py:50-66), `_get_positions_to_remove`
+ * (:68-83) and the running output index of `_create_minimized_sequence` (:94-96).
+ * `first_idx` is the global 0-based index of sample 0 (a rank's shard offset).
+ * Synchronises; afterwards lengths / record offsets are readable. */
+int gm2_plan(gm2_ctx* ctx, int64_t first_idx);
+/* As gm2_plan but leaves everything on the device and does not synchronise
+ * (gm2_emit_dev can follow on the same stream; gm2_get_* would sync). */
+int gm2_plan_async(gm2_ctx* ctx, int64_t first_idx);
+
+/* Results of the plan (host arrays owned by the caller).  lengths[s] = kept bases
+ * L_s; rec_off[s] = byte offset of record s in the concatenated image, rec_off[S] =
+ * image size.  keep_rows = the S x ceil(F/32) keep matrix (what K1 produced). */
+int gm2_get_lengths(gm2_ctx* ctx, int64_t* lengths /* S */);
+int gm2_get_record_offsets(gm2_ctx* ctx, int64_t* rec_off /* S+1 */);
+int gm2_get_keep_rows(gm2_ctx* ctx, uint32_t* keep_rows /* S*ceil(F/32) */);
+/* Total image bytes for records [s0,s1) (needs a synchronised plan). */
+int gm2_image_bytes(gm2_ctx* ctx, int64_t s0, int64_t s1, int64_t* out);
+
+/* K4 compaction gather + FASTA framing: replaces `_create_minimized_sequence`
+ * (minimizer_2.py:85-101) and the record write `f">{seq_id}\n{seq}\n"` (:476-477,
+ * :544-545) for records [s0,s1), record s0 starting at dev_out[0].  Asynchronous on
+ * the context's stream.  `cap` is checked against the image size when the plan has
+ * been synchronised, otherwise it is trusted. */
+int gm2_emit_dev(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* dev_out, int64_t cap);
+
+/* Same, delivered to CPU memory: records [s0,s1) are produced in device staging
+ * buffers in pieces of about `chunk_bytes` (0 = default) and copied to `host_out`
+ * while the next piece is being produced.  Synchronous.  `host_out` should be pinned
+ * (gm2_host_alloc) for full PCIe speed. */
+int gm2_emit_host(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* host_out, int64_t cap,
+                  int64_t chunk_bytes);
+
+/* One-call convenience used by the batch entry functions: load keep rows or ids from
+ * host memory, plan, and deliver the whole image to host memory. */
+int gm2_minimize_host(gm2_ctx* ctx, const int32_t* ids, const int64_t* off,
+                      const uint32_t* keep_rows, int64_t S, int64_t first_idx,
+                      int64_t* lengths /* S */, int64_t* rec_off /* S+1 */,
+                      uint8_t* host_out, int64_t cap, int64_t chunk_bytes);
+
+/* Pinned host memory for output buffers. */
+int gm2_host_alloc(void** out, int64_t bytes);
+int gm2_host_free(void* p);
+
+/* Diagnostics used by bench.py only: a write-only fill of `bytes` bytes with 128-bit
+ * stores (the write roofline of this device), on the context's stream. */
+int gm2_diag_fill(gm2_ctx* ctx, uint8_t* dev, int64_t bytes, uint32_t pattern);
+/* Position-dependent 64-bit hashes of n byte ranges [off[i], off[i+1]) of a device
+ * buffer, reduced on the device,
+ * mod 2^64 over the range read as little-endian 8-byte words w_k (zero padded at the
+ * end): hash = sum_k mix64(k * 0x9E3779B97F4A7C15 + w_k) with mix64 = the splitmix64
+ * finaliser.  `dev` must be 8-byte aligned.  Lets tests compare full-size images record by record with the oracle
+ * without copying 26 GB to the host.  `off` and `out` are host arrays. */
+int gm2_diag_range_hashes(gm2_ctx* ctx, const uint8_t* dev, int64_t dev_bytes,
+                          const int64_t* off /* n+1 */, int64_t n, uint64_t* out /* n */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM2_H_ */
