@@ -557,16 +557,23 @@ k_range_hashes(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t
     const int64_t o0 = off[r], n = off[r + 1] - o0;
     const int64_t nwords = (n + 7) >> 3;
     const int m = (int)(o0 & 7);
-    const unsigned long long* w64 = reinterpret_cast<const unsigned long long*>(buf + (o0 - m));
-    const int64_t avail = (buf_bytes - (o0 - m)) >> 3;          // whole aligned words readable
+    const uint8_t* abase = buf + (o0 - m);                       // 8-byte aligned (buf is)
+    const unsigned long long* w64 = reinterpret_cast<const unsigned long long*>(abase);
+    const int64_t abytes = buf_bytes - (o0 - m);                // bytes readable from abase
+    const int64_t avail = abytes >> 3;                          // whole aligned words readable
+    auto load_word = [&](int64_t k) -> unsigned long long {
+        if (k < avail) return w64[k];
+        unsigned long long w = 0;                               // partial word at the buffer's end
+        for (int b = 0; b < 8; ++b) {
+            const int64_t p = 8 * k + b;
+            if (p < abytes) w |= (unsigned long long)abase[p] << (8 * b);
+        }
+        return w;
+    };
     unsigned long long acc = 0;
     for (int64_t k = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < nwords; k += (int64_t)gridDim.y * blockDim.x) {
-        unsigned long long lo = k < avail ? w64[k] : 0ull;
-        unsigned long long w = lo;
-        if (m) {
-            const unsigned long long hi = (k + 1) < avail ? w64[k + 1] : 0ull;
-            w = (lo >> (8 * m)) | (hi << (64 - 8 * m));
-        }
+        unsigned long long w = load_word(k);
+        if (m) w = (w >> (8 * m)) | (load_word(k + 1) << (64 - 8 * m));
         const int64_t valid = n - 8 * k;
         if (valid < 8) w &= (1ull << (8 * valid)) - 1ull;
         acc += mix64((unsigned long long)k * 0x9E3779B97F4A7C15ull + w);

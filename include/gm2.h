@@ -74,7 +74,8 @@ const char* gm2_last_error(const gm2_ctx* ctx);      /* ctx may be NULL: create-
 int         gm2_configure(gm2_ctx* ctx, int key, int64_t value);
 int         gm2_query(const gm2_ctx* ctx, int key, int64_t* out);
 /* Issue this context's work on the caller's CUDA stream (cudaStream_t passed as
- * void*; NULL restores the context's own stream). */
+ * void*).  NULL restores the context's own non-blocking stream; to target the legacy
+ * default stream pass cudaStreamLegacy ((void*)0x1) explicitly. */
 int         gm2_set_stream(gm2_ctx* ctx, void* cuda_stream);
 int         gm2_sync(gm2_ctx* ctx);
 

@@ -1,0 +1,291 @@
+"""Parity of the CUDA path against the oracle and the golden fixtures.  Needs a B200: -m gpu.
+
+Everything here goes through the C-ABI (ctypes binding `_native.Context`) or the drop-in
+entry functions that sit on top of it.  Bar: bit-exact (byte/integer work).
+"""
+from __future__ import annotations
+
+import contextlib
+import hashlib
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle, genbank_reader, minimizer_oracle as mo  # noqa: E402  (checker only)
+
+import genome_minimizer_2_b200 as gm2  # noqa: E402
+from genome_minimizer_2_b200 import _native, engine, genbank, synth  # noqa: E402
+
+
+# ----------------------------------------------------------------------------------------------
+# golden fixtures through the drop-in entry functions
+# ----------------------------------------------------------------------------------------------
+def _mask_ts(data: bytes) -> str:
+    lines = data.decode().split("\n")
+    assert re.fullmatch(r"# Generated on: \d{4}-\d\d-\d\dT\d\d:\d\d:\d\d", lines[2]), lines[2]
+    lines[2] = "# Generated on: <TS>"
+    return "\n".join(lines)
+
+
+def test_single_file_entry_matches_reference(golden, golden_paths, tmp_path):
+    gb, npy = golden_paths
+    out = tmp_path / "deep" / "dir" / "out.fasta"
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ret = gm2.process_multiple_genomes_single_file(gb, npy, golden["model_name"], str(out))
+    data = _mask_ts(out.read_bytes())
+    if "single_file" in golden:
+        assert data == golden["single_file"]
+    else:
+        assert hashlib.sha256(data.encode()).hexdigest() == golden["single_file_sha256"]
+    assert buf.getvalue() == golden["single_stdout"]
+    assert ret == golden["single_return"]
+
+
+def test_multi_file_entry_matches_reference(golden, golden_paths, tmp_path):
+    gb, npy = golden_paths
+    outdir = tmp_path / "multi"
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ret = gm2.process_multiple_genomes_multiple_files(gb, npy, golden["model_name"], outdir)  # a Path, as main.py:603 passes
+    files = {fn: (outdir / fn).read_bytes() for fn in sorted(os.listdir(outdir))}
+    if "multi_files" in golden:
+        assert {k: v.decode() for k, v in files.items()} == golden["multi_files"]
+    else:
+        assert {k: hashlib.sha256(v).hexdigest() for k, v in files.items()} == golden["multi_files_sha256"]
+    assert buf.getvalue().replace(str(outdir), "<OUTDIR>") == golden["multi_stdout"]
+    assert ret == golden["multi_return"]
+
+
+def test_class_facade_matches_reference(golden, golden_paths):
+    gb, npy = golden_paths
+    cs = golden["class_sample"]
+    rec = genbank.read_genbank(gb)
+    m = gm2.GenomeMinimiser(record=rec, needed_genes_list=golden["lists"][cs["idx"]], idx=cs["idx"], model_name="x")
+    assert hashlib.sha256(m.reduced_genome_str.encode()).hexdigest() == cs["reduced_genome_str_sha256"]
+    assert [[f.location.start, f.location.end] for f in m.features] == cs["removed_gene_spans"]
+    assert m.get_reduction_stats() == cs["stats"]
+    # the path-based constructor (record_path / needed_genes_path) gives the same answer
+    m2 = gm2.GenomeMinimiser(record_path=gb, needed_genes_path=npy, idx=cs["idx"])
+    assert m2.reduced_genome_str == m.reduced_genome_str
+
+
+def test_empty_gene_list_file_divides_by_zero(tmp_path):
+    """Reference behaviour for 0 lists: preamble written, then ZeroDivisionError (minimizer_2.py:488)."""
+    g = synth.make_genome(500, 6, 3, nested=0)
+    gb = tmp_path / "g.gb"
+    synth.write_genbank(str(gb), g)
+    npy = tmp_path / "e.npy"
+    np.save(npy, np.empty(0, dtype=object), allow_pickle=True)
+    with pytest.raises(ZeroDivisionError):
+        gm2.process_multiple_genomes_single_file(str(gb), str(npy), "m", str(tmp_path / "o.fasta"))
+    assert (tmp_path / "o.fasta").read_text().startswith("# Minimized genomes generated using model: m\n# Total genomes: 0\n")
+
+
+# ----------------------------------------------------------------------------------------------
+# C-ABI level parity against the C oracle on seeded random inputs
+# ----------------------------------------------------------------------------------------------
+def _oracle_image(seq, starts, ends, rows, first_idx=0):
+    lengths, hashes, image = c_oracle.batch(seq, starts, ends, rows, first_idx=first_idx, want_image=True)
+    return lengths, hashes, image
+
+
+def _gpu_image(ctx, S):
+    n = ctx.image_bytes(0, S)
+    out = np.empty(n, dtype=np.uint8)
+    ctx.emit_host(0, S, out)
+    return out
+
+
+@pytest.mark.parametrize("G,F,seed,kw", [
+    (0, 0, 1, {}),
+    (1, 0, 2, {}),
+    (17, 3, 3, dict(nested=1)),
+    (4096, 0, 4, {}),
+    (5000, 64, 5, dict(nested=6, overlap_frac=0.5, join_genes=4)),
+    (65536, 100, 6, dict(nested=4)),            # exactly one tile
+    (65537, 100, 7, dict(nested=4)),            # one base into the second tile
+    (200_000, 33, 8, dict(nested=2, iupac_runs=5, origin_wrap=True)),
+    (300_001, 900, 9, dict(nested=30, overlap_frac=0.4, genic_frac=0.95)),
+])
+def test_keep_rows_parity_random(G, F, seed, kw):
+    g = synth.make_genome(G, F, seed, **kw)
+    starts, ends = g.starts_ends()
+    Fg = len(g.genes)
+    S = 37
+    p = np.linspace(0.0, 1.0, S)
+    keep = synth.random_keep_bool(Fg, S, p, seed=seed)
+    rows = synth.pack_keep_rows(keep) if Fg else np.zeros((S, 0), dtype=np.uint32)
+    exp_len, exp_hash, exp_img = _oracle_image(g.seq, starts, ends, rows, first_idx=9_999_990)
+    with _native.Context(0) as ctx:
+        ctx.set_reference(g.seq, starts, ends)
+        ctx.load_keep_host(rows.reshape(S, -1)) if Fg else ctx.load_keep_host(np.zeros((S, 0), dtype=np.uint32).reshape(S, 0))
+        ctx.plan(9_999_990)                      # ids cross 7 -> 8 digits inside this batch
+        assert np.array_equal(ctx.lengths(), exp_len)
+        off = ctx.record_offsets()
+        assert off[0] == 0 and off[-1] == exp_img.size
+        img = _gpu_image(ctx, S)
+        assert np.array_equal(img, exp_img)
+
+
+def test_interval_soup_parity():
+    """Arbitrary (unsorted, nested, duplicated, empty, out-of-range) intervals."""
+    rng = np.random.default_rng(77)
+    for trial in range(12):
+        G = int(rng.integers(1, 150_000))
+        F = int(rng.integers(1, 300))
+        seq = rng.integers(65, 91, G, dtype=np.uint8)
+        starts = rng.integers(-50, G + 50, F).astype(np.int64)
+        ends = starts + rng.integers(-20, max(G // 20, 30), F)
+        if trial % 3 == 0:
+            starts[0], ends[0] = 0, G                      # a gene spanning everything
+        S = 19
+        rows = synth.pack_keep_rows(rng.random((S, F)) < rng.random())
+        exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows)
+        with _native.Context(0) as ctx:
+            ctx.configure(_native.CFG_TILE_BYTES, int(rng.choice([4096, 8192, 65536, 131072])))
+            ctx.configure(_native.CFG_EMIT_WARPS, int(rng.choice([1, 4, 8, 16])))
+            ctx.set_reference(seq, starts, ends)
+            ctx.load_keep_host(rows)
+            ctx.plan(0)
+            assert np.array_equal(ctx.lengths(), exp_len)
+            assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+def test_ids_mode_matches_keep_mode_and_oracle():
+    """K1: name-id lists (duplicates, unknown ids, 1:many names) -> keep rows."""
+    g = synth.make_genome(120_000, 300, 21, nested=10, dup_name_frac=0.2, nameless_frac=0.05)
+    starts, ends = g.starts_ends()
+    table = engine.GeneTable(g.gene_names(), starts, ends)
+    rng = np.random.default_rng(3)
+    S = 64
+    keep_names = rng.random((S, table.V)) < 0.5
+    ids, off = synth.ids_csr_from_keep(keep_names, n_noise=40, V=table.V, seed=4)
+    ids = np.concatenate([ids, ids[:0]])
+    # expected keep rows: gene kept iff its name id is in the row
+    name_id = np.asarray([table.name_to_id[n] for n in table.names])
+    keep = keep_names[:, name_id]
+    rows = synth.pack_keep_rows(keep)
+    exp_len, _, exp_img = _oracle_image(g.seq, starts, ends, rows)
+    with _native.Context(0) as ctx:
+        ctx.set_reference(g.seq, starts, ends)
+        ctx.set_name_map(table.id2gene_off, table.id2gene_idx)
+        # negative and huge ids are legal noise
+        ids2 = ids.copy()
+        ctx.load_ids_host(np.concatenate([ids2, np.asarray([-1, 2**31 - 1], dtype=np.int32)]),
+                          np.concatenate([off[:-1], [off[-1] + 2]]).astype(np.int64))
+        ctx.plan(0)
+        assert np.array_equal(ctx.keep_rows(), rows)
+        assert np.array_equal(ctx.lengths(), exp_len)
+        assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+def test_chunked_and_ranged_emit_equal_whole_image():
+    g = synth.make_genome(150_000, 200, 31)
+    starts, ends = g.starts_ends()
+    S = 50
+    rows = synth.pack_keep_rows(synth.random_keep_bool(len(g.genes), S, 0.5, seed=1))
+    _, _, exp_img = _oracle_image(g.seq, starts, ends, rows)
+    with _native.Context(0) as ctx:
+        ctx.set_reference(g.seq, starts, ends)
+        ctx.load_keep_host(rows)
+        ctx.plan(0)
+        off = ctx.record_offsets()
+        whole = np.empty(off[-1], dtype=np.uint8)
+        ctx.emit_host(0, S, whole, chunk_bytes=200_000)       # forces many small staged chunks
+        assert np.array_equal(whole, exp_img)
+        for a, b in [(0, 1), (7, 19), (49, 50), (20, 20)]:
+            part = np.empty(off[b] - off[a], dtype=np.uint8)
+            ctx.emit_host(a, b, part)
+            assert np.array_equal(part, exp_img[off[a]:off[b]])
+        small = np.empty(10, dtype=np.uint8)
+        with pytest.raises(_native.Gm2Error) as ei:
+            ctx.emit_host(0, S, small)
+        assert ei.value.code == _native.ERR_CAPACITY
+
+
+def test_engine_drain_delivers_every_byte_once():
+    g = synth.make_genome(100_000, 120, 41)
+    rec_lists = synth.make_gene_lists(g, 23, 0.5, seed=5, extra_names=10)
+    starts, ends = g.starts_ends()
+    table = engine.GeneTable(g.gene_names(), starts, ends)
+    eng = engine.MinimizerEngine(seq=g.seq, table=table)
+    try:
+        lengths = eng.plan_lists(rec_lists)
+        got = []
+        total = eng.drain(lambda a, b, v: got.append((a, b, v.tobytes())), max_bytes=300_000)
+        img = b"".join(x[2] for x in got)
+        assert total == len(img)
+        assert [x[0] for x in got][0] == 0 and got[-1][1] == 23
+        keep = np.stack([mo.keep_vector(table.names, l) for l in rec_lists])
+        exp_len, _, exp_img = _oracle_image(g.seq, starts, ends, synth.pack_keep_rows(keep))
+        assert np.array_equal(lengths, exp_len)
+        assert img == exp_img.tobytes()
+    finally:
+        eng.close()
+
+
+def test_device_image_hashes_match_oracle_k12_shape():
+    """K-12-shaped genome, device-resident image, compared record by record through the
+    device-side range hash (no 100+ MB host copies) and byte-for-byte on a subset."""
+    import torch
+    g = synth.make_genome(seed=1)
+    starts, ends = g.starts_ends()
+    S = 48
+    rows = synth.pack_keep_rows(synth.random_keep_bool(len(g.genes), S, 0.5, seed=2))
+    exp_len, exp_hash, _ = c_oracle.batch(g.seq, starts, ends, rows)
+    with _native.Context(0) as ctx:
+        ctx.set_reference(g.seq, starts, ends)
+        ctx.load_keep_host(rows)
+        ctx.plan(0)
+        assert np.array_equal(ctx.lengths(), exp_len)
+        off = ctx.record_offsets()
+        img = torch.empty(int(off[-1]), dtype=torch.uint8, device="cuda:0")
+        ctx.emit_dev(0, S, img.data_ptr(), img.numel())
+        ctx.sync()
+        got = ctx.diag_range_hashes(img.data_ptr(), img.numel(), off)
+        assert np.array_equal(got, exp_hash)
+        # byte-exact on three records
+        for s in (0, 17, S - 1):
+            _, _, one = c_oracle.batch(g.seq, starts, ends, rows[s:s + 1], first_idx=s, want_image=True)
+            assert np.array_equal(img[int(off[s]):int(off[s + 1])].cpu().numpy(), one)
+        # size-independent properties: every record ends in '\n', starts with '>', no byte outside ACGT/header
+        host = img[:int(off[1])].cpu().numpy()
+        assert host[0] == ord(">") and host[-1] == 10
+        # all-kept and none-kept rows bracket every length
+        allk = synth.pack_keep_rows(np.ones((1, len(g.genes)), bool))
+        none = synth.pack_keep_rows(np.zeros((1, len(g.genes)), bool))
+        ctx.load_keep_host(np.concatenate([allk, none]))
+        ctx.plan(0)
+        L = ctx.lengths()
+        assert L[0] == g.G and L[1] <= exp_len.min()
+
+
+def test_header_prefix_and_store_policy_variants():
+    g = synth.make_genome(70_000, 80, 51)
+    starts, ends = g.starts_ends()
+    S = 9
+    rows = synth.pack_keep_rows(synth.random_keep_bool(len(g.genes), S, 0.4, seed=3))
+    _, _, exp_img = c_oracle.batch(g.seq, starts, ends, rows, prefix="Other_prefix|", want_image=True)
+    for policy in (0, 1):
+        with _native.Context(0) as ctx:
+            ctx.configure(_native.CFG_STORE_POLICY, policy)
+            ctx.set_header_prefix("Other_prefix|")
+            ctx.set_reference(g.seq, starts, ends)
+            ctx.load_keep_host(rows)
+            ctx.plan(0)
+            assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+def test_call_order_errors_are_reported():
+    with _native.Context(0) as ctx:
+        with pytest.raises(_native.Gm2Error) as ei:
+            ctx.plan(0)
+        assert ei.value.code == _native.ERR_STATE
+        with pytest.raises(_native.Gm2Error):
+            ctx.configure(_native.CFG_TILE_BYTES, 1000)
