@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--emit-warps", type=int, default=0)
     ap.add_argument("--emit-batch", type=int, default=-1)
     ap.add_argument("--store-policy", type=int, default=-1)
+    ap.add_argument("--emit-order", type=int, default=-1)
+    ap.add_argument("--emit-debug", type=int, default=0, help="timing experiments only (wrong output)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -275,6 +277,11 @@ def main():
         ctx.configure(_native.CFG_EMIT_BATCH, args.emit_batch)
     if args.store_policy >= 0:
         ctx.configure(_native.CFG_STORE_POLICY, args.store_policy)
+    if args.emit_order >= 0:
+        ctx.configure(_native.CFG_ORDER, args.emit_order)
+    if args.emit_debug:
+        ctx.configure(_native.CFG_DEBUG, args.emit_debug)
+        args.verify = 0
     # a real (non-default) torch stream: the kernels are launched on it and the CUDA events below are
     # recorded on it.  (torch's default stream has handle 0, which gm2_set_stream reads as "own stream".)
     stream = torch.cuda.Stream(dev)

@@ -17,7 +17,7 @@ from . import build as _build
 ABI_VERSION = 1
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM = -1, -2, -3, -4, -5
-CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY = 1, 2, 3, 4, 5
+CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY, CFG_RUN_TABLE, CFG_DEBUG, CFG_ORDER = 1, 2, 3, 4, 5, 6, 7, 8
 Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS = 1, 2, 3, 4, 5, 6, 7
 
 _c = ctypes
@@ -54,6 +54,7 @@ SIGNATURES = {
     "gm2_host_alloc": (_c.c_int, [_c.POINTER(_P), _I64]),
     "gm2_host_free": (_c.c_int, [_P]),
     "gm2_diag_fill": (_c.c_int, [_P, _P, _I64, _c.c_uint32]),
+    "gm2_diag_fill_streams": (_c.c_int, [_P, _P, _I64, _I64, _c.c_int32, _I64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
     "gm2_diag_range_hashes": (_c.c_int, [_P, _P, _I64, _P, _I64, _P]),
 }
 
@@ -292,6 +293,9 @@ class Context:
     # -- diagnostics ------------------------------------------------------------------------------
     def diag_fill(self, dev_ptr: int, nbytes: int, pattern: int = 0x41414141):
         self._ck(self._lib.gm2_diag_fill(self._h, int(dev_ptr), int(nbytes), pattern))
+
+    def diag_fill_streams(self, dev_ptr, nrec, stride, ntile, chunk, batch, warps, order=0, vec32=0):
+        self._ck(self._lib.gm2_diag_fill_streams(self._h, int(dev_ptr), nrec, stride, ntile, chunk, batch, warps, order, vec32))
 
     def diag_range_hashes(self, dev_ptr: int, dev_bytes: int, off: np.ndarray) -> np.ndarray:
         off = np.ascontiguousarray(off, dtype=np.int64)

@@ -58,22 +58,25 @@ struct gm2_ctx {
     int emit_warps = 8;
     int emit_batch = 0;
     int packing_req = 0;
-    int store_policy = 0;
+    int store_policy = 1;
+    int rt_cap = 64;
+    int debug = 0;
+    int order = 1;
     HeaderPrefix prefix;
 
     // reference
     bool have_ref = false;
     int64_t G = 0;
     int32_t F = 0, FW = 0;
-    int ntiles = 0, nseg = 0, nslots = 0, SW = 0;
+    int ntiles = 0, nseg = 0, nslots = 0, SW = 0, max_tile_slots = 0;
     int packing = 1;
     uint8_t* d_seq = nullptr;
     int32_t *d_tile_slot = nullptr, *d_slot_src = nullptr, *d_slot_len = nullptr;
-    int32_t *d_cov_off = nullptr, *d_cov_idx = nullptr;
+    int2* d_slot_cov = nullptr; int32_t* d_cov_ovf = nullptr;
 
     // name map
     int32_t V = 0;
-    int32_t *d_map_off = nullptr, *d_map_idx = nullptr;
+    int32_t *d_first_gene = nullptr, *d_next_same = nullptr;
 
     // samples
     int64_t S = 0;
@@ -174,90 +177,131 @@ __device__ __forceinline__ int ndigits_u64(unsigned long long v) {
 
 // ------------------------------------------------------------------------------------------
 // K1  keep-mask builder: name-id lists -> F-bit keep rows          (minimizer_2.py:59-63)
-//   one warp per sample; the row is assembled in shared memory with atomicOr (an id
-//   maps to 0..n genes through the static CSR), then written out coalesced.
+//   One warp per sample, CTAs loop over groups of samples.  The static name table is a
+//   linked list through the genes (first_gene[id] -> next_same_name[g] -> ...), staged in
+//   shared memory when it fits, so an id costs one coalesced global load plus shared-memory
+//   lookups; the row is assembled in shared memory with atomicOr and written out coalesced.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V,
-                const int32_t* __restrict__ map_off, const int32_t* __restrict__ map_idx,
-                int FW, uint32_t* __restrict__ keep)
+#define K1_WARPS 8
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V, int32_t F,
+                const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
+                int FW, uint32_t* __restrict__ keep, int map_in_smem)
 {
-    extern __shared__ uint32_t k1_rows[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int64_t s = (int64_t)blockIdx.x * wpb + warp;
-    if (s >= S) return;                                   // warp-uniform, no block barriers below
-    uint32_t* row = k1_rows + (size_t)warp * FW;
-    for (int i = lane; i < FW; i += 32) row[i] = 0u;
-    __syncwarp();
-    const int64_t b = off[s], e = off[s + 1];
-    for (int64_t i = b + lane; i < e; i += 32) {
-        const int32_t id = __ldg(ids + i);
-        if ((uint32_t)id < (uint32_t)V) {
-            const int k1 = __ldg(map_off + id + 1);
-            for (int k = __ldg(map_off + id); k < k1; ++k) {
-                const int g = __ldg(map_idx + k);
-                atomicOr(&row[g >> 5], 1u << (g & 31));
+    extern __shared__ uint32_t k1_sm[];
+    uint32_t* rows = k1_sm;                                          // K1_WARPS x FW
+    const int32_t* fg = first_gene;
+    const int32_t* nx = next_same;
+    if (map_in_smem) {
+        int32_t* s_fg = reinterpret_cast<int32_t*>(k1_sm + (size_t)K1_WARPS * FW);
+        int32_t* s_nx = s_fg + V;
+        for (int i = threadIdx.x; i < V; i += blockDim.x) s_fg[i] = first_gene[i];
+        for (int i = threadIdx.x; i < F; i += blockDim.x) s_nx[i] = next_same[i];
+        fg = s_fg; nx = s_nx;
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* row = rows + (size_t)warp * FW;
+    for (int64_t s = (int64_t)blockIdx.x * K1_WARPS + warp; s < S; s += (int64_t)gridDim.x * K1_WARPS) {
+        for (int i = lane; i < FW; i += 32) row[i] = 0u;
+        __syncwarp();
+        const int64_t b = off[s], e = off[s + 1];
+        for (int64_t i0 = b; i0 < e; i0 += 128) {
+            int32_t id[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + lane + 32 * u;
+                id[u] = i < e ? __ldg(ids + i) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if ((uint32_t)id[u] < (uint32_t)V) {
+                    for (int g = fg[id[u]]; g >= 0; g = nx[g]) atomicOr(&row[g >> 5], 1u << (g & 31));
+                }
             }
         }
+        __syncwarp();
+        uint32_t* dst = keep + (size_t)s * FW;
+        for (int i = lane; i < FW; i += 32) dst[i] = row[i];
+        __syncwarp();
     }
-    __syncwarp();
-    uint32_t* dst = keep + (size_t)s * FW;
-    for (int i = lane; i < FW; i += 32) dst[i] = row[i];
 }
 
 // ------------------------------------------------------------------------------------------
 // K2 + K3a  plan: per sample, segment kept-flags and the exclusive scan of kept lengths
 //   (minimizer_2.py:75-80 union-of-ranges, :94-96 running output index)
-//   One CTA per sample.  Segment slots are laid out per genome tile, each tile's slots
-//   padded to a multiple of 32 so that one ballot == one stored word and k_emit reads
-//   whole words.  A warp reduces one tile at a time; warp 0 then scans the tile sums.
+//   One CTA per PLAN_NS samples (the static tables are read once for all of them).  Segment
+//   slots are laid out per genome tile, each tile's slots padded to a multiple of 32 so that
+//   one ballot == one stored word and k_emit reads whole words.  Per slot the covering genes
+//   are inlined as a pair (x, y): -1 = none; y <= -2 points into an overflow list for the rare
+//   slot covered by more than two genes.  A warp reduces one tile at a time; warp 0 then scans
+//   the tile sums of each sample.
 // ------------------------------------------------------------------------------------------
+#define PLAN_NS 4
+__device__ __forceinline__ bool keep_bit(const uint32_t* row, int g) {
+    return g < 0 ? true : ((row[g >> 5] >> (g & 31)) & 1u) != 0u;
+}
+
 __global__ void __launch_bounds__(256)
 k_plan(int64_t S, int FW, const uint32_t* __restrict__ keep, int ntiles,
        const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_len,
-       const int32_t* __restrict__ cov_off, const int32_t* __restrict__ cov_idx,
+       const int2* __restrict__ slot_cov, const int32_t* __restrict__ cov_ovf,
        int SW, uint32_t* __restrict__ segkept, int32_t* __restrict__ tile_off,
        int64_t* __restrict__ lengths, int64_t* __restrict__ rec_size,
        int64_t first_idx, int prefix_len)
 {
     extern __shared__ uint32_t plan_sm[];
-    uint32_t* row = plan_sm;                       // FW words
-    int32_t* tl = (int32_t*)(plan_sm + FW);        // ntiles
-    const int64_t s = blockIdx.x;
+    uint32_t* rows = plan_sm;                                   // PLAN_NS x FW
+    int32_t* tl = (int32_t*)(plan_sm + (size_t)PLAN_NS * FW);   // PLAN_NS x ntiles
+    const int64_t sbase = (int64_t)blockIdx.x * PLAN_NS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
-    const uint32_t* krow = keep + (size_t)s * FW;
-    for (int i = threadIdx.x; i < FW; i += blockDim.x) row[i] = krow[i];
-    __syncthreads();
-
-    uint32_t* sk = segkept + (size_t)s * SW;
-    for (int t = warp; t < ntiles; t += nwarps) {
-        const int sb = __ldg(tile_slot + t), se = __ldg(tile_slot + t + 1);   // multiples of 32
-        int sum = 0;
-        for (int slot = sb + lane; slot < se; slot += 32) {
-            const int len = __ldg(slot_len + slot);
-            bool kept = len > 0;                      // padding slots have len 0
-            if (kept) {
-                const int k1 = __ldg(cov_off + slot + 1);
-                for (int k = __ldg(cov_off + slot); k < k1; ++k) {
-                    const int g = __ldg(cov_idx + k);
-                    if (!((row[g >> 5] >> (g & 31)) & 1u)) { kept = false; break; }
-                }
-            }
-            const uint32_t w = __ballot_sync(FULL_MASK, kept);
-            if (lane == 0) sk[slot >> 5] = w;
-            sum += kept ? len : 0;
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) tl[t] = sum;
+    for (int i = threadIdx.x; i < PLAN_NS * FW; i += blockDim.x) {
+        const int64_t s = sbase + i / FW;
+        rows[i] = s < S ? keep[(size_t)s * FW + (i % FW)] : 0u;
     }
     __syncthreads();
-    if (warp == 0) {
+
+    for (int t = warp; t < ntiles; t += nwarps) {
+        const int sb = __ldg(tile_slot + t), se = __ldg(tile_slot + t + 1);   // multiples of 32
+        int sum[PLAN_NS];
+#pragma unroll
+        for (int k = 0; k < PLAN_NS; ++k) sum[k] = 0;
+        for (int slot = sb + lane; slot < se; slot += 32) {
+            const int len = __ldg(slot_len + slot);
+            const int2 cv = __ldg(slot_cov + slot);
+#pragma unroll
+            for (int k = 0; k < PLAN_NS; ++k) {
+                const uint32_t* row = rows + (size_t)k * FW;
+                bool kept = len > 0 && keep_bit(row, cv.x);          // padding slots have len 0
+                if (kept) {
+                    if (cv.y >= -1) kept = keep_bit(row, cv.y);
+                    else {
+                        const int32_t* o = cov_ovf + (-cv.y - 2);
+                        const int n = __ldg(o);
+                        for (int j = 1; j <= n && kept; ++j) kept = keep_bit(row, __ldg(o + j));
+                    }
+                }
+                const uint32_t w = __ballot_sync(FULL_MASK, kept);
+                if (lane == 0 && sbase + k < S) segkept[(size_t)(sbase + k) * SW + (slot >> 5)] = w;
+                sum[k] += kept ? len : 0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PLAN_NS; ++k) {
+            const int v = warp_sum(sum[k]);
+            if (lane == 0) tl[k * ntiles + t] = v;
+        }
+    }
+    __syncthreads();
+    if (warp < PLAN_NS && sbase + warp < S) {
+        const int64_t s = sbase + warp;
+        const int32_t* mytl = tl + warp * ntiles;
         int carry = 0;
         int32_t* to = tile_off + (size_t)s * ntiles;
         for (int base = 0; base < ntiles; base += 32) {
             const int t = base + lane;
-            const int v = t < ntiles ? tl[t] : 0;
+            const int v = t < ntiles ? mytl[t] : 0;
             const int incl = warp_incl_scan(v, lane);
             if (t < ntiles) to[t] = carry + incl - v;
             carry += __shfl_sync(FULL_MASK, incl, 31);
@@ -386,7 +430,12 @@ struct EmitParams {
     uint8_t* out;
     int64_t s0, s1;
     int64_t first_idx;
-    int tile_bytes, ntiles, SW, batch, nbatch, store_policy;
+    int tile_bytes, ntiles, SW, batch, nbatch;
+    int rt_cap;            // run-table entries per warp (shared memory)
+    int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
+    int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
+    int debug;             // timing experiments only (wrong output): 1 no phase B, 2 no phase A stores,
+                           // 4 phase A stores without shared loads, 8 build the run table once per warp
     HeaderPrefix prefix;
 };
 
@@ -394,83 +443,201 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// shared-memory accessors on 32-bit shared-window addresses.  Tile / slot-table reads are plain
+// (read-only after the CTA barrier, free to be scheduled); run-table accesses are volatile with a
+// memory clobber because the table is rewritten per (sample, tile) around __syncwarp().
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 rt_load(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rt_store(uint32_t a, int x, int y) {
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void rt_store_x(uint32_t a, int x) {
+    asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(x) : "memory");
+}
+
+// POLICY 1 = streaming (evict-first) stores: the image is written once and never re-read here.
 template <int POLICY>
 __device__ __forceinline__ void st128(uint8_t* p, const uint4& v) {
     if (POLICY == 1) __stcs(reinterpret_cast<uint4*>(p), v);
     else *reinterpret_cast<uint4*>(p) = v;
 }
-
-// Warp-cooperative copy of n bytes from shared memory (byte offset a in `tile`) to global d.
 template <int POLICY>
-__device__ __forceinline__ void copy_run(const uint8_t* __restrict__ tile, int a, uint8_t* __restrict__ d,
-                                         int n, int lane)
-{
-    int h = (int)((16u - (uint32_t)((uintptr_t)d & 15u)) & 15u);
-    if (h > n) h = n;
-    if (lane < h) d[lane] = tile[a + lane];
-    a += h; d += h; n -= h;
-    const int nb = n >> 4;
-    const int mis = a & 15;
-    const uint8_t* q = tile + (a - mis);
-    const int k = mis >> 2;
-    const int sh = (mis & 3) * 8;
-    if (mis == 0) {
-        for (int v = lane; v < nb; v += 32)
-            st128<POLICY>(d + 16 * v, *reinterpret_cast<const uint4*>(q + 16 * v));
-    } else {
-        for (int v = lane; v < nb; v += 32) {
-            const uint4 lo = *reinterpret_cast<const uint4*>(q + 16 * v);
-            const uint4 hi = *reinterpret_cast<const uint4*>(q + 16 * v + 16);
-            uint4 o;
-            switch (k) {
-            case 0:
-                o.x = __funnelshift_r(lo.x, lo.y, sh); o.y = __funnelshift_r(lo.y, lo.z, sh);
-                o.z = __funnelshift_r(lo.z, lo.w, sh); o.w = __funnelshift_r(lo.w, hi.x, sh); break;
-            case 1:
-                o.x = __funnelshift_r(lo.y, lo.z, sh); o.y = __funnelshift_r(lo.z, lo.w, sh);
-                o.z = __funnelshift_r(lo.w, hi.x, sh); o.w = __funnelshift_r(hi.x, hi.y, sh); break;
-            case 2:
-                o.x = __funnelshift_r(lo.z, lo.w, sh); o.y = __funnelshift_r(lo.w, hi.x, sh);
-                o.z = __funnelshift_r(hi.x, hi.y, sh); o.w = __funnelshift_r(hi.y, hi.z, sh); break;
-            default:
-                o.x = __funnelshift_r(lo.w, hi.x, sh); o.y = __funnelshift_r(hi.x, hi.y, sh);
-                o.z = __funnelshift_r(hi.y, hi.z, sh); o.w = __funnelshift_r(hi.z, hi.w, sh); break;
-            }
-            st128<POLICY>(d + 16 * v, o);
-        }
-    }
-    const int t = n & 15;
-    if (lane < t) d[16 * nb + lane] = tile[a + 16 * nb + lane];
+__device__ __forceinline__ void st8(uint8_t* p, uint32_t v) {
+    if (POLICY == 1) __stcs(p, (uint8_t)v);
+    else *p = (uint8_t)v;
 }
 
+// One whole 32-byte sector from one lane (STG.256).
+__device__ __forceinline__ void st256(uint8_t* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// Interior of one kept run: nb destination-aligned 16-byte vectors, lanes strided by 32.
+// qa = this lane's 16-byte aligned shared address at or below its first source byte,
+// K = word phase (0..3), sh = byte phase in bits.
+template <int POLICY, int K>
+__device__ __forceinline__ void copy_vectors(uint32_t qa, uint8_t* __restrict__ d, int nb, int sh, int lane)
+{
+    for (int v = lane; v < nb; v += 32, qa += 512, d += 512) {
+        const uint4 lo = lds128(qa);
+        const uint4 hi = lds128(qa + 16);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint4 o;
+        o.x = __funnelshift_r(w[K], w[K + 1], sh);
+        o.y = __funnelshift_r(w[K + 1], w[K + 2], sh);
+        o.z = __funnelshift_r(w[K + 2], w[K + 3], sh);
+        o.w = __funnelshift_r(w[K + 3], w[K + 4], sh);
+        st128<POLICY>(d, o);
+    }
+}
+
+// 16 bytes from an arbitrarily aligned shared address (per-lane alignment).
+__device__ __forceinline__ uint4 fetch16(uint32_t a) {
+    const uint32_t a4 = a & ~3u;
+    const int sh = (int)(a & 3u) * 8;
+    const uint32_t w0 = lds32(a4), w1 = lds32(a4 + 4), w2 = lds32(a4 + 8), w3 = lds32(a4 + 12), w4 = lds32(a4 + 16);
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                      __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+__device__ __forceinline__ uint32_t low_bytes_mask(int n) {          // n bytes from the low end, n clamped to 0..4
+    return n >= 4 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
+}
+
+// One batch of kept runs of a (sample, tile): table entry r = {Q_r, S_r}, entry nr = {end, -}.
+//   Q = destination offset in "Q space" (bytes from base32, a 32-byte aligned global pointer),
+//   S = source byte offset inside the shared-memory tile.  Output is contiguous: run r covers
+//   [Q_r, Q_{r+1}).
+// The warp writes ONE ASCENDING STREAM in units of 32-byte sectors, each sector exactly once and
+// in address order (measured with store-only models, profiles/r01_emit_experiments.md: a sector
+// written out of stream, microseconds after its neighbours, costs 11-19 % of the bandwidth because
+// its line has already left L2; written in stream it is free):
+//   for each run r, in order
+//     - if the run starts inside a sector, that sector (tail of run r-1 and earlier, head of run r
+//       and later) is gathered cooperatively, lane j <-> byte j, and leaves as one coalesced store;
+//     - then every whole sector inside the run, 128-bit stores, source re-phased by funnel shifts;
+//   finally the partial last sector.  Bytes outside [Q_0, Q_nr) belong to the neighbouring
+//   tile / batch (another warp) and are never touched.
 template <int POLICY>
-__global__ void __launch_bounds__(1024)
+__device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, int nr, uint8_t* __restrict__ base32, int lane, int debug)
+{
+    __syncwarp();
+    int2 e = rt_load(rt_a), en = rt_load(rt_a + 8);
+    const int q_first = e.x, q_last = rt_load(rt_a + 8 * nr).x;
+    int wnext = q_first >> 5;                               // first sector not yet written
+    for (int r = 0; r <= nr; ++r) {
+        // r == nr is the pseudo-run [q_last, q_last): only its boundary sector (the partial tail)
+        const int2 en2 = rt_load(rt_a + 8 * (r + 2 <= nr ? r + 2 : nr));          // prefetch
+        const int W = e.x >> 5;
+        if ((e.x & 31) && W >= wnext && !(debug & 1)) {
+            const int pos = (W << 5) + lane;
+            if (pos >= q_first && pos < q_last) {
+                int rr = r; int2 ec = e;
+                if (pos < e.x) { do { --rr; ec = rt_load(rt_a + 8 * rr); } while (pos < ec.x); }
+                else { int qn = en.x; while (pos >= qn) { ++rr; ec = rt_load(rt_a + 8 * rr); qn = rt_load(rt_a + 8 * (rr + 1)).x; } }
+                st8<POLICY>(base32 + pos, lds8(tile_a + (uint32_t)(ec.y + (pos - ec.x))));
+            }
+            wnext = W + 1;
+        }
+        if (r < nr) {
+            const int sa = max((e.x + 31) >> 5, wnext), sb = en.x >> 5;               // whole sectors [sa, sb)
+            const int va = sa << 1, nb = (sb - sa) << 1;                              // in 16-byte vectors
+            if (nb > 0) {
+                wnext = sb;
+                const int src = e.y + (16 * va - e.x);
+                const int mis = src & 15;
+                const uint32_t qa = tile_a + (uint32_t)(src - mis) + 16u * lane;
+                uint8_t* d = base32 + 16 * (int64_t)(va + lane);
+                const int sh = (mis & 3) * 8;
+                if (debug & 6) {
+                    if (debug & 4) { for (int v = lane; v < nb; v += 32, d += 512) st128<POLICY>(d, make_uint4(sh, mis, nb, va)); }
+                    else { uint32_t q = qa, acc = 0; for (int v = lane; v < nb; v += 32, q += 512) { const uint4 t = lds128(q); acc ^= t.x ^ t.w; }
+                           if (acc == 0x12345u) st128<POLICY>(d, make_uint4(acc, 0, 0, 0)); }
+                } else if (mis == 0) {
+                    uint32_t q = qa;
+                    for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
+                } else {
+                    switch (mis >> 2) {
+                    case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
+                    case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
+                    case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
+                    default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
+                    }
+                }
+            }
+        }
+        e = en; en = en2;
+    }
+    __syncwarp();
+}
+
+#define EMIT_FRONT_PAD 32
+#define EMIT_BACK_PAD  64
+
+template <int POLICY, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 k_emit(const EmitParams p)
 {
-    extern __shared__ __align__(128) uint8_t tile_sm[];   // tile_bytes + 32 (over-read pad)
+    // dynamic shared memory: 16 B front pad | tile bytes | 32 B over-read pad | slot tables | per-warp run tables
+    extern __shared__ __align__(128) uint8_t dsm[];
     __shared__ __align__(8) unsigned long long bar;
 
-    const int tile = blockIdx.x / p.nbatch;
-    const int b = blockIdx.x - tile * p.nbatch;
+    const int ntl = p.ntiles > 0 ? p.ntiles : 1;
+    const int tile = p.order ? (int)(blockIdx.x % ntl) : (int)(blockIdx.x / p.nbatch);
+    const int b = p.order ? (int)(blockIdx.x / ntl) : (int)(blockIdx.x - tile * p.nbatch);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const bool have_tile = p.ntiles > 0;
+    const int sl0 = have_tile ? __ldg(p.tile_slot + tile) : 0;
+    const int nslots = have_tile ? __ldg(p.tile_slot + tile + 1) - sl0 : 0;
+    const int nwords = nslots >> 5;
+    const int tile_base = tile * p.tile_bytes;
+
+    const uint32_t dsm_a = smem_u32(dsm);
+    const uint32_t tile_a = dsm_a + EMIT_FRONT_PAD;
+    const uint32_t len_a = tile_a + (uint32_t)p.tile_bytes + EMIT_BACK_PAD;
+    const uint32_t src_a = len_a + 4u * (uint32_t)p.slot_cap;
+    const uint32_t rt_a = src_a + 4u * (uint32_t)p.slot_cap + (uint32_t)warp * (uint32_t)(p.rt_cap + 2) * 8u;
+    int32_t* sm_len = reinterpret_cast<int32_t*>(dsm + EMIT_FRONT_PAD + p.tile_bytes + EMIT_BACK_PAD);
+    int32_t* sm_src = sm_len + p.slot_cap;
+    const bool slots_staged = nslots <= p.slot_cap;
 
     if (have_tile) {
         const uint32_t bar_a = smem_u32(&bar);
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
             const uint32_t bytes = (uint32_t)p.tile_bytes;
             const uint8_t* src = p.seq + (size_t)tile * p.tile_bytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(tile_sm)), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
+                         :: "r"(tile_a), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
         }
-        // every thread waits for phase 0 of the barrier (the TMA's complete_tx)
-        uint32_t done = 0;
+        if (slots_staged) {
+            for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+                sm_len[i] = __ldg(p.slot_len + sl0 + i);
+                sm_src[i] = __ldg(p.slot_src + sl0 + i) - tile_base;
+            }
+        }
+        __syncthreads();                      // barrier init + slot tables visible to every thread
+        uint32_t done = 0;                    // wait for phase 0 of the mbarrier (the TMA's complete_tx)
         while (!done) {
             asm volatile("{\n\t.reg .pred p;\n\t"
                          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -481,14 +648,29 @@ k_emit(const EmitParams p)
 
     const int64_t sb = p.s0 + (int64_t)b * p.batch;
     const int64_t se = sb + p.batch < p.s1 ? sb + p.batch : p.s1;
-    const int sl0 = have_tile ? __ldg(p.tile_slot + tile) : 0;
-    const int sl1 = have_tile ? __ldg(p.tile_slot + tile + 1) : 0;
-    const int tile_base = tile * p.tile_bytes;
     const int last_tile = p.ntiles > 0 ? p.ntiles - 1 : 0;
     const int64_t img0 = __ldg(p.rec_off + p.s0);
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    for (int64_t s = sb + warp; s < se; s += nwarps) {
-        uint8_t* rec = p.out + (__ldg(p.rec_off + s) - img0);
+    // per-sample metadata is fetched one sample ahead: record offset, this tile's output offset,
+    // the sample's length (last tile only) and ALL kept-bit words of the tile in one coalesced load
+    int64_t m_roff = 0; int m_toff = 0; uint32_t m_words = 0u;
+    auto load_meta = [&](int64_t s) {
+        m_roff = __ldg(p.rec_off + s);
+        if (have_tile) {
+            m_toff = __ldg(p.tile_off + (size_t)s * p.ntiles + tile);
+            m_words = lane < nwords ? __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + lane) : 0u;
+        }
+    };
+    int dbg_nr = 0, dbg_q = 0;
+    int64_t s = sb + warp;
+    if (s < se) load_meta(s);
+    while (s < se) {
+        const int64_t roff = m_roff; const int toff = m_toff; const uint32_t words = m_words;
+        const int64_t sn = s + nwarps;
+        if (sn < se) load_meta(sn);
+
+        uint8_t* rec = p.out + (roff - img0);
         const unsigned long long num = (unsigned long long)(p.first_idx + s + 1);
         const int nd = ndigits_u64(num);
         const int hl = p.prefix.len + nd + 1;
@@ -503,32 +685,41 @@ k_emit(const EmitParams p)
         }
         uint8_t* seqout = rec + hl;
         if (have_tile) {
-            uint8_t* d = seqout + __ldg(p.tile_off + (size_t)s * p.ntiles + tile);
-            const uint32_t* sk = p.segkept + (size_t)s * p.SW;
-            for (int slot0 = sl0; slot0 < sl1; slot0 += 32) {
-                const uint32_t w = __ldg(sk + (slot0 >> 5));          // warp-uniform
-                const int slot = slot0 + lane;
-                const int len = __ldg(p.slot_len + slot);
-                const int src = __ldg(p.slot_src + slot) - tile_base;
+            const int A = (int)((uintptr_t)seqout & 31u);
+            uint8_t* base32 = seqout - A;
+            int q = toff + A;
+            int nr = 0;
+            uint32_t carry = 0u;
+            if ((p.debug & 8) && s != sb + warp) {           // timing experiment: reuse the first sample's table
+                nr = dbg_nr; q = dbg_q;
+            } else
+            for (int c = 0; c < nwords; ++c) {
+                if (nr + 17 > p.rt_cap) {                       // table full: flush what we have
+                    if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
+                    emit_runs<POLICY>(tile_a, rt_a, nr, base32, lane, p.debug);
+                    nr = 0; carry = 0u;
+                }
+                const uint32_t w = c < 32 ? __shfl_sync(FULL_MASK, words, c)
+                                          : __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + c);   // warp-uniform
+                int len, src;
+                if (slots_staged) { len = (int)lds32(len_a + 4u * (32 * c + lane)); src = (int)lds32(src_a + 4u * (32 * c + lane)); }
+                else { len = __ldg(p.slot_len + sl0 + 32 * c + lane); src = __ldg(p.slot_src + sl0 + 32 * c + lane) - tile_base; }
                 const int x = ((w >> lane) & 1u) ? len : 0;
                 const int incl = warp_incl_scan(x, lane);
-                const int excl = incl - x;
-                uint32_t m = w;
-                while (m) {
-                    const int a = __ffs(m) - 1;
-                    const uint32_t t = ~(m >> a);
-                    const int cnt = t ? (__ffs(t) - 1) : 32;
-                    const int bl = a + cnt - 1;
-                    const int rsrc = __shfl_sync(FULL_MASK, src, a);
-                    const int rdst = __shfl_sync(FULL_MASK, excl, a);
-                    const int rend = __shfl_sync(FULL_MASK, incl, bl);
-                    copy_run<POLICY>(tile_sm, rsrc, d + rdst, rend - rdst, lane);
-                    m = cnt >= 32 ? 0u : (m & ~(((1u << cnt) - 1u) << a));
-                }
-                d += __shfl_sync(FULL_MASK, incl, 31);
+                const uint32_t starts = w & ~((w << 1) | carry);
+                carry = w >> 31;
+                if ((starts >> lane) & 1u) rt_store(rt_a + 8u * (nr + __popc(starts & lt_mask)), q + incl - x, src);
+                nr += __popc(starts);
+                q += __shfl_sync(FULL_MASK, incl, 31);
+            }
+            if (p.debug & 8) { dbg_nr = nr; dbg_q = q; }
+            if (nr > 0) {
+                if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
+                emit_runs<POLICY>(tile_a, rt_a, nr, base32, lane, p.debug);
             }
         }
         if (tile == last_tile && lane == 0) seqout[__ldg(p.lengths + s)] = (uint8_t)'\n';
+        s = sn;
     }
 }
 
@@ -541,6 +732,39 @@ k_fill(uint4* __restrict__ dst, int64_t nvec, uint32_t pattern)
     const uint4 v = make_uint4(pattern, pattern, pattern, pattern);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) dst[i] = v;
+}
+
+// Store-only model of k_emit's write pattern: CTA = (tile, batch of samples), each warp streams
+// `chunk` contiguous bytes of record s at offset tile*chunk, records `stride` bytes apart.
+__global__ void __launch_bounds__(256)
+k_fill_streams(uint8_t* __restrict__ dst, int64_t nrec, int64_t stride, int ntile, int64_t chunk, int batch, int nbatch,
+               int order, int vec32)
+{
+    const int tile = order ? (int)(blockIdx.x % ntile) : (int)(blockIdx.x / nbatch);
+    const int b = order ? (int)(blockIdx.x / ntile) : (int)(blockIdx.x - tile * nbatch);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int64_t sb = (int64_t)b * batch, se = sb + batch < nrec ? sb + batch : nrec;
+    const uint4 v = make_uint4(0x41414141u, 0x43434343u, 0x47474747u, 0x54545454u);
+    for (int64_t s = sb + warp; s < se; s += nwarps) {
+        // vec32 bits: 1 = 256-bit stores; bits 8.. = misalignment of the chunk start in bytes (multiple of 32);
+        // bits 16.. = fragment length in bytes (0 = none): after every fragment 32 bytes are skipped,
+        // modelling a run boundary whose sector is written separately
+        const int mis = (vec32 >> 8) & 0xff, frag = vec32 >> 16;
+        uint8_t* p = dst + s * stride + (int64_t)tile * chunk + mis;
+        const int64_t n = chunk - mis;
+        if (frag) {
+            for (int64_t f0 = 0; f0 + frag <= n; f0 += frag) {
+                for (int64_t o = 16 * lane; o + 16 <= frag - 32; o += 512) *reinterpret_cast<uint4*>(p + f0 + o) = v;
+                if ((vec32 & 4) && lane == ((f0 / frag) & 31)) st256(p + f0 + frag - 32, v, v);     // in-stream, one lane
+                if ((vec32 & 8) && lane < 2) *reinterpret_cast<uint4*>(p + f0 + frag - 32 + 16 * lane) = v;   // in-stream, two lanes
+            }
+            if ((vec32 & 2)) {                                  // the skipped sectors, one lane each, afterwards
+                for (int64_t f0 = (int64_t)frag * (lane + 1) - 32; f0 + 32 <= n; f0 += (int64_t)frag * 32) st256(p + f0, v, v);
+            }
+        }
+        else if (vec32 & 1) { for (int64_t o = 32 * lane; o + 32 <= n; o += 1024) st256(p + o, v, v); }
+        else                { for (int64_t o = 16 * lane; o + 16 <= n; o += 512) *reinterpret_cast<uint4*>(p + o) = v; }
+    }
 }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
@@ -656,8 +880,8 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     if (!c) return GM2_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_cov_off, c->d_cov_idx,
-                     c->d_map_off, c->d_map_idx, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
+    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
+                     c->d_first_gene, c->d_next_same, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
                      c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
     for (void* p : frees) if (p) cudaFree(p);
@@ -682,7 +906,7 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
             return fail(c, GM2_ERR_INVALID, "tile bytes must be a multiple of 4096 in [4096, 196608]");
         c->tile_bytes = (int)value; return GM2_OK;
     case GM2_CFG_EMIT_WARPS:
-        if (value < 1 || value > 32) return fail(c, GM2_ERR_INVALID, "emit warps must be in 1..32");
+        if (value < 1 || value > 8) return fail(c, GM2_ERR_INVALID, "emit warps must be in 1..8");
         c->emit_warps = (int)value; return GM2_OK;
     case GM2_CFG_EMIT_BATCH:
         if (value < 0 || value > (1 << 20)) return fail(c, GM2_ERR_INVALID, "emit batch out of range");
@@ -693,6 +917,14 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     case GM2_CFG_STORE_POLICY:
         if (value != 0 && value != 1) return fail(c, GM2_ERR_INVALID, "store policy must be 0 or 1");
         c->store_policy = (int)value; return GM2_OK;
+    case GM2_CFG_ORDER:
+        if (value != 0 && value != 1) return fail(c, GM2_ERR_INVALID, "order must be 0 (tile-major) or 1 (sample-major)");
+        c->order = (int)value; return GM2_OK;
+    case GM2_CFG_DEBUG:
+        c->debug = (int)value; return GM2_OK;
+    case GM2_CFG_RUN_TABLE:
+        if (value < 32 || value > 1024) return fail(c, GM2_ERR_INVALID, "run table entries must be in 32..1024");
+        c->rt_cap = (int)value; return GM2_OK;
     default:
         return fail(c, GM2_ERR_INVALID, "gm2_configure: unknown key");
     }
@@ -782,12 +1014,11 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
 
     // slot layout: each tile's segments padded to a multiple of 32 slots
     std::vector<int32_t> tile_slot((size_t)ntiles + 1, 0);
-    std::vector<int32_t> slot_src, slot_len, cov_off, cov_idx;
+    std::vector<int32_t> slot_src, slot_len, cov_ovf;
+    std::vector<int2> slot_cov;
     slot_src.reserve((size_t)nseg + 32 * (size_t)ntiles);
     slot_len.reserve(slot_src.capacity());
-    cov_off.reserve(slot_src.capacity() + 1);
-    cov_idx.reserve(seg_cov.size());
-    cov_off.push_back(0);
+    slot_cov.reserve(slot_src.capacity());
     int j = 0;
     for (int t = 0; t < ntiles; ++t) {
         tile_slot[t] = (int32_t)slot_src.size();
@@ -795,16 +1026,29 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
         while (j < nseg && bp[j] < tend) {
             slot_src.push_back((int32_t)bp[j]);
             slot_len.push_back((int32_t)(bp[j + 1] - bp[j]));
-            for (int64_t k = seg_cov_off[j]; k < seg_cov_off[j + 1]; ++k) cov_idx.push_back(seg_cov[(size_t)k]);
-            cov_off.push_back((int32_t)cov_idx.size());
+            {
+                const int64_t k0 = seg_cov_off[j], nc = seg_cov_off[j + 1] - k0;
+                int2 cv = make_int2(-1, -1);
+                if (nc >= 1) cv.x = seg_cov[(size_t)k0];
+                if (nc == 2) cv.y = seg_cov[(size_t)k0 + 1];
+                if (nc > 2) {                               // rare: spill the rest to the overflow list
+                    if (cov_ovf.size() + (size_t)nc > (size_t)0x7ffffff0) return fail(c, GM2_ERR_INVALID, "gm2_set_reference: cover table too large");
+                    cv.y = -2 - (int32_t)cov_ovf.size();
+                    cov_ovf.push_back((int32_t)(nc - 1));
+                    for (int64_t k = 1; k < nc; ++k) cov_ovf.push_back(seg_cov[(size_t)(k0 + k)]);
+                }
+                slot_cov.push_back(cv);
+            }
             ++j;
         }
         while (slot_src.size() % 32) {
             slot_src.push_back((int32_t)tend); slot_len.push_back(0);
-            cov_off.push_back((int32_t)cov_idx.size());
+            slot_cov.push_back(make_int2(-1, -1));
         }
     }
     tile_slot[ntiles] = (int32_t)slot_src.size();
+    int max_tile_slots = 0;
+    for (int t = 0; t < ntiles; ++t) max_tile_slots = std::max(max_tile_slots, tile_slot[t + 1] - tile_slot[t]);
 
     // upload
     if (c->d_seq) { cudaFree(c->d_seq); c->d_seq = nullptr; }
@@ -816,12 +1060,12 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
     if ((rc = dev_upload(c, &c->d_tile_slot, tile_slot))) return rc;
     if ((rc = dev_upload(c, &c->d_slot_src, slot_src))) return rc;
     if ((rc = dev_upload(c, &c->d_slot_len, slot_len))) return rc;
-    if ((rc = dev_upload(c, &c->d_cov_off, cov_off))) return rc;
-    if ((rc = dev_upload(c, &c->d_cov_idx, cov_idx))) return rc;
+    if ((rc = dev_upload(c, &c->d_slot_cov, slot_cov))) return rc;
+    if ((rc = dev_upload(c, &c->d_cov_ovf, cov_ovf))) return rc;
 
     c->G = G; c->F = F; c->FW = (F + 31) / 32;
     c->ntiles = ntiles; c->nseg = nseg; c->nslots = (int)slot_src.size(); c->SW = c->nslots / 32;
-    c->packing = 1;
+    c->packing = 1; c->max_tile_slots = max_tile_slots;
     c->have_ref = true; c->planned = false; c->host_plan = false; c->mode = 0; c->S = 0;
     return GM2_OK;
 }
@@ -836,10 +1080,22 @@ GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx,
     if (n > 0 && !idx) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: idx is NULL");
     for (int32_t i = 0; i < n; ++i) if (idx[i] < 0 || idx[i] >= c->F) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: gene index out of range");
     CU(c, cudaSetDevice(c->device));
-    std::vector<int32_t> o(off, off + V + 1), x(idx, idx + n);
+    // device form: first_gene[id] -> next_same_name[g] -> ... -> -1 (list in CSR order)
+    std::vector<int32_t> first((size_t)V, -1), next((size_t)c->F, -1);
+    std::vector<char> seen((size_t)c->F, 0);
+    for (int32_t id = 0; id < V; ++id) {
+        int32_t prev = -1;
+        for (int32_t k = off[id]; k < off[id + 1]; ++k) {
+            const int32_t g = idx[k];
+            if (seen[g]) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: a gene is listed under two names");
+            seen[g] = 1;
+            if (prev < 0) first[id] = g; else next[prev] = g;
+            prev = g;
+        }
+    }
     int rc;
-    if ((rc = dev_upload(c, &c->d_map_off, o))) return rc;
-    if ((rc = dev_upload(c, &c->d_map_idx, x))) return rc;
+    if ((rc = dev_upload(c, &c->d_first_gene, first))) return rc;
+    if ((rc = dev_upload(c, &c->d_next_same, next))) return rc;
     c->V = V;
     return GM2_OK;
 }
@@ -856,7 +1112,7 @@ static int begin_samples(gm2_ctx* c, int64_t S, const char* who) {
 
 GM2_API int gm2_load_ids_host(gm2_ctx* c, const int32_t* ids, const int64_t* off, int64_t S) {
     int rc = begin_samples(c, S, "gm2_load_ids_host"); if (rc) return rc;
-    if (!c->d_map_off) return fail(c, GM2_ERR_STATE, "gm2_load_ids_host: call gm2_set_name_map first");
+    if (!c->d_first_gene) return fail(c, GM2_ERR_STATE, "gm2_load_ids_host: call gm2_set_name_map first");
     if (!off) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_host: off is NULL");
     if (off[0] != 0) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_host: off[0] must be 0");
     for (int64_t s = 0; s < S; ++s) if (off[s + 1] < off[s]) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_host: offsets must be non-decreasing");
@@ -873,7 +1129,7 @@ GM2_API int gm2_load_ids_host(gm2_ctx* c, const int32_t* ids, const int64_t* off
 
 GM2_API int gm2_load_ids_dev(gm2_ctx* c, const int32_t* ids, const int64_t* off, int64_t S, int64_t n_ids) {
     int rc = begin_samples(c, S, "gm2_load_ids_dev"); if (rc) return rc;
-    if (!c->d_map_off) return fail(c, GM2_ERR_STATE, "gm2_load_ids_dev: call gm2_set_name_map first");
+    if (!c->d_first_gene) return fail(c, GM2_ERR_STATE, "gm2_load_ids_dev: call gm2_set_name_map first");
     if (!off || (n_ids > 0 && !ids) || n_ids < 0) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_dev: bad arguments");
     c->ids = ids; c->ids_off = off; c->S = S; c->mode = 1;
     return GM2_OK;
@@ -923,21 +1179,28 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;
         keep = c->own_keep;
         if (S > 0 && c->FW > 0) {
-            const int wpb = 8;
-            const size_t sm = (size_t)wpb * c->FW * 4;
-            if (sm > 48 * 1024) CU(c, cudaFuncSetAttribute(k_keep_from_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            const int64_t blocks = (S + wpb - 1) / wpb;
-            k_keep_from_ids<<<(unsigned)blocks, wpb * 32, sm, c->stream>>>(c->ids, c->ids_off, S, c->V, c->d_map_off,
-                                                                         c->d_map_idx, c->FW, c->own_keep);
+            const size_t rows_b = (size_t)K1_WARPS * c->FW * 4;
+            const size_t map_b = ((size_t)c->V + (size_t)c->F) * 4;
+            const int map_in_smem = rows_b + map_b <= 96 * 1024;
+            const size_t sm = rows_b + (map_in_smem ? map_b : 0);
+            if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: too many genes for the keep-row staging buffer");
+            CU(c, cudaFuncSetAttribute(k_keep_from_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            const int64_t groups = (S + K1_WARPS - 1) / K1_WARPS;
+            const int64_t blocks = std::min<int64_t>(groups, (int64_t)c->sm_count * (map_in_smem ? 4 : 8));
+            k_keep_from_ids<<<(unsigned)blocks, K1_WARPS * 32, sm, c->stream>>>(c->ids, c->ids_off, S, c->V, c->F,
+                                                                              c->d_first_gene, c->d_next_same, c->FW,
+                                                                              c->own_keep, map_in_smem);
             LAUNCH_CHECK(c, "k_keep_from_ids");
         }
     }
     if (S > 0) {
-        const size_t sm = ((size_t)c->FW + (size_t)c->ntiles) * 4;
-        if (sm > 48 * 1024) CU(c, cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_plan<<<(unsigned)S, 256, sm, c->stream>>>(S, c->FW, keep, c->ntiles, c->d_tile_slot, c->d_slot_len,
-                                                    c->d_cov_off, c->d_cov_idx, c->SW, c->d_segkept, c->d_tile_off,
-                                                    c->d_len, c->d_rec_size, first_idx, c->prefix.len);
+        const size_t sm = ((size_t)c->FW + (size_t)c->ntiles) * 4 * PLAN_NS;
+        if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: genome has too many genes/tiles for one CTA's shared memory");
+        CU(c, cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        const int64_t blocks = (S + PLAN_NS - 1) / PLAN_NS;
+        k_plan<<<(unsigned)blocks, 256, sm, c->stream>>>(S, c->FW, keep, c->ntiles, c->d_tile_slot, c->d_slot_len,
+                                                         c->d_slot_cov, c->d_cov_ovf, c->SW, c->d_segkept, c->d_tile_off,
+                                                         c->d_len, c->d_rec_size, first_idx, c->prefix.len);
         LAUNCH_CHECK(c, "k_plan");
     }
     {
@@ -1034,15 +1297,18 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     p.segkept = c->d_segkept; p.tile_off = c->d_tile_off; p.lengths = c->d_len; p.rec_off = c->d_rec_off;
     p.out = dev_out; p.s0 = s0; p.s1 = s1; p.first_idx = c->first_idx;
     p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW; p.batch = (int)batch; p.nbatch = (int)nbatch;
-    p.store_policy = c->store_policy; p.prefix = c->prefix;
-    const size_t sm = (size_t)c->tile_bytes + 32;
-    if (c->store_policy == 1) {
-        CU(c, cudaFuncSetAttribute(k_emit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_emit<1><<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
-    } else {
-        CU(c, cudaFuncSetAttribute(k_emit<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_emit<0><<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
-    }
+    p.rt_cap = c->rt_cap;
+    p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
+    p.prefix = c->prefix; p.debug = c->debug; p.order = c->order;
+    const size_t sm = 32 + (size_t)c->tile_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 8;
+    if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
+    // register budget follows the shared-memory footprint: small tiles -> 4+ CTAs/SM (64 regs),
+    // large tiles -> 3 CTAs/SM (up to 85 regs)
+    const bool dense = sm <= 56 * 1024;
+    void (*kern)(const EmitParams) =
+        c->store_policy == 1 ? (dense ? k_emit<1, 4> : k_emit<1, 3>) : (dense ? k_emit<0, 4> : k_emit<0, 3>);
+    CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
     LAUNCH_CHECK(c, "k_emit");
     return GM2_OK;
 }
@@ -1134,6 +1400,18 @@ GM2_API int gm2_diag_fill(gm2_ctx* c, uint8_t* dev, int64_t bytes, uint32_t patt
     const int blocks = c->sm_count * 16;
     k_fill<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<uint4*>(dev), nvec, pattern);
     LAUNCH_CHECK(c, "k_fill");
+    return GM2_OK;
+}
+
+GM2_API int gm2_diag_fill_streams(gm2_ctx* c, uint8_t* dev, int64_t nrec, int64_t stride, int32_t ntile, int64_t chunk,
+                                  int32_t batch, int32_t warps, int32_t order, int32_t vec32)
+{
+    if (!c || !dev || nrec <= 0 || ntile <= 0 || batch <= 0 || warps < 1 || warps > 8 || ((uintptr_t)dev & 31) || (stride & 31) || (chunk & 31))
+        return fail(c, GM2_ERR_INVALID, "gm2_diag_fill_streams: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    const int64_t nbatch = (nrec + batch - 1) / batch;
+    k_fill_streams<<<(unsigned)(nbatch * ntile), warps * 32, 0, c->stream>>>(dev, nrec, stride, ntile, chunk, batch, (int)nbatch, order, vec32);
+    LAUNCH_CHECK(c, "k_fill_streams");
     return GM2_OK;
 }
 

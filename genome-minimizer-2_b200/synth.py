@@ -145,8 +145,10 @@ def make_genome(G: int = K12_G, F: int = K12_F, seed: int = 1, *, overlap_frac: 
         genes[int(i)].name = genes[int(j)].name
     for i in rng.permutation(n)[:int(round(nameless_frac * n))]:
         genes[int(i)].name = None
-    if n >= 3:
-        genes[n // 2].extra_names = ["syn" + genes[n // 2].locus_tag]
+    for k in range(n // 2, n):                    # one gene carries a second /gene value (a synonym)
+        if genes[k].name is not None:
+            genes[k].extra_names = ["syn" + genes[k].locus_tag]
+            break
     return SynthGenome(seq=seq, genes=genes, name=name)
 
 

@@ -47,10 +47,13 @@ extern "C" {
 
 /* gm2_configure keys */
 #define GM2_CFG_TILE_BYTES    1  /* reference bases staged per CTA (multiple of 4096; before set_reference) */
-#define GM2_CFG_EMIT_WARPS    2  /* warps per emit CTA (1..32)                               */
+#define GM2_CFG_EMIT_WARPS    2  /* warps per emit CTA (1..8)                                */
 #define GM2_CFG_EMIT_BATCH    3  /* samples per emit CTA; 0 = choose from S and the SM count */
 #define GM2_CFG_PACKING       4  /* 0 auto, 1 byte/base, 2 two-bit (ACGT-only references)    */
-#define GM2_CFG_STORE_POLICY  5  /* 0 default stores, 1 streaming (st.global.cs)             */
+#define GM2_CFG_STORE_POLICY  5  /* 0 plain stores, 1 streaming st.global.cs (default)       */
+#define GM2_CFG_RUN_TABLE     6  /* kept-run table entries per warp in shared memory (32..1024) */
+#define GM2_CFG_ORDER         8  /* emit CTA order: 0 tile-major, 1 sample-major (default)   */
+#define GM2_CFG_DEBUG         7  /* timing experiments only: non-zero values produce WRONG output  */
 
 /* gm2_query keys */
 #define GM2_Q_SM_COUNT        1
@@ -155,6 +158,12 @@ int gm2_host_free(void* p);
 /* Diagnostics used by bench.py only: a write-only fill of `bytes` bytes with 128-bit
  * stores (the write roofline of this device), on the context's stream. */
 int gm2_diag_fill(gm2_ctx* ctx, uint8_t* dev, int64_t bytes, uint32_t pattern);
+/* Diagnostics: a store-only model of the emit kernel's write pattern (nrec records `stride` bytes
+ * apart, each written as ntile chunks of `chunk` bytes by one warp per (record, chunk), CTAs =
+ * (chunk index, batch of records)).  Used to separate "what the memory system gives this pattern"
+ * from "what the kernel's instructions cost". */
+int gm2_diag_fill_streams(gm2_ctx* ctx, uint8_t* dev, int64_t nrec, int64_t stride, int32_t ntile,
+                          int64_t chunk, int32_t batch, int32_t warps, int32_t order, int32_t vec32);
 /* Position-dependent 64-bit hashes of n byte ranges [off[i], off[i+1]) of a device
  * buffer, reduced on the device,
  * mod 2^64 over the range read as little-endian 8-byte words w_k (zero padded at the

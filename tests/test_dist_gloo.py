@@ -1,0 +1,85 @@
+"""World-size-2 gloo test of the sharded entry point's host logic (shard ranges, length
+all-gather, global offsets, pwrite placement).  No GPU here, so the per-rank compute is a test
+double backed by the oracle; the product's own engine is exercised by the -m gpu tests."""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden
+
+
+class OracleEngine:
+    """Stand-in with MinimizerEngine's plan_lists / drain surface (tests only)."""
+
+    def __init__(self, record):
+        from oracle import minimizer_oracle as mo
+        self.mo, self.record = mo, record
+        self.images, self.first = [], 0
+
+    def plan_lists(self, lists, first_idx=0):
+        self.first = first_idx
+        seqs = [self.mo.minimize_literal(self.record, l) for l in lists]
+        self.images = [self.mo.record_bytes(first_idx + i, s.encode()) for i, s in enumerate(seqs)]
+        return np.asarray([len(s) for s in seqs], dtype=np.int64)
+
+    def drain(self, sink, max_bytes=0):
+        for i, img in enumerate(self.images):                # one record per chunk: worst case for offsets
+            sink(i, i + 1, np.frombuffer(img, dtype=np.uint8))
+
+
+def _worker(rank, world, port, case_name, out_path, ret_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import tempfile
+        from oracle import genbank_reader
+        from genome_minimizer_2_b200 import dist as gdist
+        case = load_golden(case_name)
+        with tempfile.NamedTemporaryFile("w", suffix=".gb", delete=False) as fh:
+            fh.write(case["genbank"])
+        rec = genbank_reader.read_genbank(fh.name)
+        os.unlink(fh.name)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ret = gdist.run_single_file_sharded(rec, case["lists"], case["model_name"], out_path,
+                                                make_engine=lambda: OracleEngine(rec), timestamp="<TS>")
+        with open(f"{ret_path}.{rank}", "w") as fh:
+            json.dump({"ret": ret, "stdout": buf.getvalue()}, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(case_name, tmp_path, world=2):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "sharded.fasta")
+    retp = str(tmp_path / "ret")
+    mp.spawn(_worker, args=(world, port, case_name, out, retp), nprocs=world, join=True)
+    case = load_golden(case_name)
+    assert open(out, "rb").read().decode() == case["single_file"]
+    r = [json.load(open(f"{retp}.{k}")) for k in range(world)]
+    assert all(x["ret"] == case["single_return"] for x in r)
+    assert r[0]["stdout"] == case["single_stdout"]
+    assert all(x["stdout"] == "" for x in r[1:])
+
+
+def test_two_ranks_reproduce_the_reference_file_kat(tmp_path):
+    _run("kat_appB", tmp_path)
+
+
+def test_two_ranks_hundred_and_one_samples(tmp_path):
+    _run("hundred_and_one", tmp_path)          # ids cross 9->10 and 99->100 digits inside shards
+
+
+def test_three_ranks_uneven_shards(tmp_path):
+    _run("rand_small_1", tmp_path, world=3)    # 17 samples over 3 ranks

@@ -149,7 +149,7 @@ def test_interval_soup_parity():
         exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows)
         with _native.Context(0) as ctx:
             ctx.configure(_native.CFG_TILE_BYTES, int(rng.choice([4096, 8192, 65536, 131072])))
-            ctx.configure(_native.CFG_EMIT_WARPS, int(rng.choice([1, 4, 8, 16])))
+            ctx.configure(_native.CFG_EMIT_WARPS, int(rng.choice([1, 2, 4, 8])))
             ctx.set_reference(seq, starts, ends)
             ctx.load_keep_host(rows)
             ctx.plan(0)
@@ -289,3 +289,52 @@ def test_call_order_errors_are_reported():
         assert ei.value.code == _native.ERR_STATE
         with pytest.raises(_native.Gm2Error):
             ctx.configure(_native.CFG_TILE_BYTES, 1000)
+
+
+def test_dense_tiny_genes_exercise_table_flush_and_global_slot_path():
+    """Thousands of tiny genes inside one tile: more slots than the shared slot table holds
+    (global fallback), run tables flushed many times, runs shorter than one 16-byte vector."""
+    rng = np.random.default_rng(123)
+    G = 70_000
+    F = 6_000
+    seq = rng.integers(65, 91, G, dtype=np.uint8)
+    starts = np.sort(rng.integers(0, G - 12, F)).astype(np.int64)
+    ends = starts + rng.integers(1, 12, F)
+    S = 21
+    rows = synth.pack_keep_rows(rng.random((S, F)) < np.linspace(0.05, 0.95, S)[:, None])
+    exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows)
+    for rt_cap, warps in ((32, 8), (64, 4), (1024, 2)):
+        with _native.Context(0) as ctx:
+            ctx.configure(_native.CFG_RUN_TABLE, rt_cap)
+            ctx.configure(_native.CFG_EMIT_WARPS, warps)
+            ctx.set_reference(seq, starts, ends)
+            assert ctx.query(_native.Q_NUM_SLOTS) > 4096
+            ctx.load_keep_host(rows)
+            ctx.plan(0)
+            assert np.array_equal(ctx.lengths(), exp_len)
+            assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+def test_many_genes_cover_one_segment():
+    """Segments covered by far more than two genes (overflow cover lists)."""
+    rng = np.random.default_rng(9)
+    G = 20_000
+    F = 40
+    seq = rng.integers(65, 91, G, dtype=np.uint8)
+    starts = rng.integers(0, 2_000, F).astype(np.int64)
+    ends = G - rng.integers(0, 2_000, F).astype(np.int64)       # all 40 genes overlap in the middle
+    S = 33
+    keep = rng.random((S, F)) < 0.9
+    keep[0] = True
+    keep[1] = False
+    keep[2] = True
+    keep[2, 17] = False
+    rows = synth.pack_keep_rows(keep)
+    exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows)
+    with _native.Context(0) as ctx:
+        ctx.set_reference(seq, starts, ends)
+        ctx.load_keep_host(rows)
+        ctx.plan(0)
+        assert np.array_equal(ctx.lengths(), exp_len)
+        assert exp_len[0] == G
+        assert np.array_equal(_gpu_image(ctx, S), exp_img)
