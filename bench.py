@@ -500,7 +500,7 @@ def main():
                    "output": f"device-resident FASTA image, {image_bytes/1e9:.2f} GB per GPU per step",
                    "l2": "no flush needed: each step writes an image >> 126 MB L2",
                    "sharding": "samples; reference replicated; all-gather of image sizes only",
-                   "tile_bytes": args.tile_bytes or 65536, "kept_bases_per_gpu": kept_bases},
+                   "tile_bytes": args.tile_bytes or 49152, "kept_bases_per_gpu": kept_bases},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "verify": verify,
     }

@@ -39,6 +39,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_ROOT, "include"), "-o", LIB, SRC]
+    if os.environ.get("GM2_EMIT_DEBUG"):          # timing knock-outs in k_emit (wrong output): experiments only
+        cmd.insert(1, "-DGM2_EMIT_DEBUG")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

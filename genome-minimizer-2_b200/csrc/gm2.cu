@@ -54,7 +54,7 @@ struct gm2_ctx {
     uint64_t launches = 0;
 
     // configuration
-    int tile_bytes = 65536;
+    int tile_bytes = 49152;        // 4 CTAs/SM of 8 warps with the 64-register kernel variant: best measured (profiles/)
     int emit_warps = 8;
     int emit_batch = 0;
     int packing_req = 0;
@@ -497,6 +497,7 @@ __device__ __forceinline__ void st256(uint8_t* p, const uint4& a, const uint4& b
 template <int POLICY, int K>
 __device__ __forceinline__ void copy_vectors(uint32_t qa, uint8_t* __restrict__ d, int nb, int sh, int lane)
 {
+#pragma unroll 1
     for (int v = lane; v < nb; v += 32, qa += 512, d += 512) {
         const uint4 lo = lds128(qa);
         const uint4 hi = lds128(qa + 16);
@@ -522,7 +523,7 @@ __device__ __forceinline__ uint32_t low_bytes_mask(int n) {          // n bytes 
     return n >= 4 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
 }
 
-// One batch of kept runs of a (sample, tile): table entry r = {Q_r, S_r}, entry nr = {end, -}.
+// One batch of kept runs of a (sample, tile): table A entry r = {Q_r, S_r}, entry nr = {end, -}.
 //   Q = destination offset in "Q space" (bytes from base32, a 32-byte aligned global pointer),
 //   S = source byte offset inside the shared-memory tile.  Output is contiguous: run r covers
 //   [Q_r, Q_{r+1}).
@@ -534,57 +535,100 @@ __device__ __forceinline__ uint32_t low_bytes_mask(int n) {          // n bytes 
 //     - if the run starts inside a sector, that sector (tail of run r-1 and earlier, head of run r
 //       and later) is gathered cooperatively, lane j <-> byte j, and leaves as one coalesced store;
 //     - then every whole sector inside the run, 128-bit stores, source re-phased by funnel shifts;
-//   finally the partial last sector.  Bytes outside [Q_0, Q_nr) belong to the neighbouring
-//   tile / batch (another warp) and are never touched.
+//   finally the partial last sector (pseudo-run nr).  Bytes outside [Q_0, Q_nr) belong to the
+//   neighbouring tile / batch (another warp) and are never touched.
+// Everything that is uniform per run is computed ONCE, lane r <-> run r, into table B
+//   {x: dst offset of the first whole sector, y: #16-byte vectors | flags, z: src offset of that
+//    sector, w: Q_r}, so the run loop costs one broadcast 128-bit shared load plus the copy.
+#define RUN_HAS_BOUNDARY 0x40000000
+#define RUN_SIMPLE       0x20000000
+#define RUN_COUNT_MASK   0x00ffffff
+
+__device__ __forceinline__ int4 rtb_load(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rtb_store(uint32_t a, int x, int y, int z, int w) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 template <int POLICY>
-__device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, int nr, uint8_t* __restrict__ base32, int lane, int debug)
+__device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32_t rtb_a, int nr,
+                                          uint8_t* __restrict__ base32, int lane, int debug)
 {
     __syncwarp();
-    int2 e = rt_load(rt_a), en = rt_load(rt_a + 8);
-    const int q_first = e.x, q_last = rt_load(rt_a + 8 * nr).x;
-    int wnext = q_first >> 5;                               // first sector not yet written
-    for (int r = 0; r <= nr; ++r) {
-        // r == nr is the pseudo-run [q_last, q_last): only its boundary sector (the partial tail)
-        const int2 en2 = rt_load(rt_a + 8 * (r + 2 <= nr ? r + 2 : nr));          // prefetch
-        const int W = e.x >> 5;
-        if ((e.x & 31) && W >= wnext && !(debug & 1)) {
-            const int pos = (W << 5) + lane;
-            if (pos >= q_first && pos < q_last) {
-                int rr = r; int2 ec = e;
-                if (pos < e.x) { do { --rr; ec = rt_load(rt_a + 8 * rr); } while (pos < ec.x); }
-                else { int qn = en.x; while (pos >= qn) { ++rr; ec = rt_load(rt_a + 8 * rr); qn = rt_load(rt_a + 8 * (rr + 1)).x; } }
-                st8<POLICY>(base32 + pos, lds8(tile_a + (uint32_t)(ec.y + (pos - ec.x))));
-            }
-            wnext = W + 1;
+    const int q_first = rt_load(rt_a).x, q_last = rt_load(rt_a + 8 * nr).x;
+    // ---- table B, lane-parallel
+    for (int r = lane; r <= nr; r += 32) {
+        const int2 er = rt_load(rt_a + 8 * r);
+        const int qn = r < nr ? rt_load(rt_a + 8 * (r + 1)).x : er.x;
+        const int qp = r > 0 ? rt_load(rt_a + 8 * (r - 1)).x : q_first;
+        const int W = er.x >> 5;
+        int flags = 0;
+        if ((er.x & 31) && !(r > 0 && (qp >> 5) == W && (qp & 31))) {        // first boundary inside sector W owns it
+            flags = RUN_HAS_BOUNDARY;
+            if ((r == 0 || qp <= (W << 5)) && (r == nr || qn >= (W << 5) + 32)) flags |= RUN_SIMPLE;
         }
-        if (r < nr) {
-            const int sa = max((e.x + 31) >> 5, wnext), sb = en.x >> 5;               // whole sectors [sa, sb)
-            const int va = sa << 1, nb = (sb - sa) << 1;                              // in 16-byte vectors
-            if (nb > 0) {
-                wnext = sb;
-                const int src = e.y + (16 * va - e.x);
-                const int mis = src & 15;
-                const uint32_t qa = tile_a + (uint32_t)(src - mis) + 16u * lane;
-                uint8_t* d = base32 + 16 * (int64_t)(va + lane);
-                const int sh = (mis & 3) * 8;
-                if (debug & 6) {
-                    if (debug & 4) { for (int v = lane; v < nb; v += 32, d += 512) st128<POLICY>(d, make_uint4(sh, mis, nb, va)); }
-                    else { uint32_t q = qa, acc = 0; for (int v = lane; v < nb; v += 32, q += 512) { const uint4 t = lds128(q); acc ^= t.x ^ t.w; }
-                           if (acc == 0x12345u) st128<POLICY>(d, make_uint4(acc, 0, 0, 0)); }
-                } else if (mis == 0) {
-                    uint32_t q = qa;
-                    for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
-                } else {
-                    switch (mis >> 2) {
-                    case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
-                    case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
-                    case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
-                    default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
-                    }
+        const int sa = (er.x + 31) >> 5, sb = qn >> 5;
+        const int nb = sb > sa ? (sb - sa) << 1 : 0;
+        rtb_store(rtb_a + 16 * r, sa << 5, nb | flags, er.y + ((sa << 5) - er.x), er.x);
+    }
+    __syncwarp();
+    // ---- the stream
+    int4 t = rtb_load(rtb_a);
+    int dA = 0;
+    for (int r = 0; r <= nr; ++r) {
+        const int4 tn = rtb_load(rtb_a + 16 * (r < nr ? r + 1 : nr));        // prefetch
+        const int dB = t.z - t.x;                                            // S_r - Q_r
+#ifdef GM2_EMIT_DEBUG
+        if ((t.y & RUN_HAS_BOUNDARY) && !(debug & 1)) {
+#else
+        if (t.y & RUN_HAS_BOUNDARY) {
+#endif
+            const int pos = (t.w & ~31) + lane;
+            if (pos >= q_first && pos < q_last) {
+                int src;
+                if (t.y & RUN_SIMPLE) {
+                    src = pos + (pos < t.w ? dA : dB);
+                } else {                                   // three or more runs meet in this sector
+                    int rr = r; int2 ec = rt_load(rt_a + 8 * rr);
+                    if (pos < ec.x) { do { --rr; ec = rt_load(rt_a + 8 * rr); } while (pos < ec.x); }
+                    else { int qn = rt_load(rt_a + 8 * (rr + 1)).x;
+                           while (pos >= qn) { ++rr; ec = rt_load(rt_a + 8 * rr); qn = rt_load(rt_a + 8 * (rr + 1)).x; } }
+                    src = ec.y + (pos - ec.x);
+                }
+                st8<POLICY>(base32 + pos, lds8(tile_a + (uint32_t)src));
+            }
+        }
+        const int nb = t.y & RUN_COUNT_MASK;
+        if (nb > 0) {
+            const int mis = t.z & 15;
+            const uint32_t qa = tile_a + (uint32_t)(t.z - mis) + 16u * lane;
+            uint8_t* d = base32 + t.x + 16 * lane;
+            const int sh = (mis & 3) * 8;
+#ifdef GM2_EMIT_DEBUG
+            if (debug & 6) {
+                if (debug & 4) { for (int v = lane; v < nb; v += 32, d += 512) st128<POLICY>(d, make_uint4(sh, mis, nb, r)); }
+                else { uint32_t q = qa, acc = 0; for (int v = lane; v < nb; v += 32, q += 512) { const uint4 tt = lds128(q); acc ^= tt.x ^ tt.w; }
+                       if (acc == 0x12345u) st128<POLICY>(d, make_uint4(acc, 0, 0, 0)); }
+            } else
+#endif
+            if (mis == 0) {
+                uint32_t q = qa;
+#pragma unroll 1
+                for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
+            } else {
+                switch (mis >> 2) {
+                case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
+                case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
+                case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
+                default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
                 }
             }
         }
-        e = en; en = en2;
+        dA = dB;
+        t = tn;
     }
     __syncwarp();
 }
@@ -614,7 +658,8 @@ k_emit(const EmitParams p)
     const uint32_t tile_a = dsm_a + EMIT_FRONT_PAD;
     const uint32_t len_a = tile_a + (uint32_t)p.tile_bytes + EMIT_BACK_PAD;
     const uint32_t src_a = len_a + 4u * (uint32_t)p.slot_cap;
-    const uint32_t rt_a = src_a + 4u * (uint32_t)p.slot_cap + (uint32_t)warp * (uint32_t)(p.rt_cap + 2) * 8u;
+    const uint32_t rt_a = src_a + 4u * (uint32_t)p.slot_cap + (uint32_t)warp * (uint32_t)(p.rt_cap + 2) * 24u;   // table A (8 B) + table B (16 B) per entry
+    const uint32_t rtb_a = rt_a + (uint32_t)(p.rt_cap + 2) * 8u;
     int32_t* sm_len = reinterpret_cast<int32_t*>(dsm + EMIT_FRONT_PAD + p.tile_bytes + EMIT_BACK_PAD);
     int32_t* sm_src = sm_len + p.slot_cap;
     const bool slots_staged = nslots <= p.slot_cap;
@@ -696,7 +741,7 @@ k_emit(const EmitParams p)
             for (int c = 0; c < nwords; ++c) {
                 if (nr + 17 > p.rt_cap) {                       // table full: flush what we have
                     if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                    emit_runs<POLICY>(tile_a, rt_a, nr, base32, lane, p.debug);
+                    emit_runs<POLICY>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
                     nr = 0; carry = 0u;
                 }
                 const uint32_t w = c < 32 ? __shfl_sync(FULL_MASK, words, c)
@@ -715,7 +760,7 @@ k_emit(const EmitParams p)
             if (p.debug & 8) { dbg_nr = nr; dbg_q = q; }
             if (nr > 0) {
                 if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                emit_runs<POLICY>(tile_a, rt_a, nr, base32, lane, p.debug);
+                emit_runs<POLICY>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
             }
         }
         if (tile == last_tile && lane == 0) seqout[__ldg(p.lengths + s)] = (uint8_t)'\n';
@@ -923,7 +968,7 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     case GM2_CFG_DEBUG:
         c->debug = (int)value; return GM2_OK;
     case GM2_CFG_RUN_TABLE:
-        if (value < 32 || value > 1024) return fail(c, GM2_ERR_INVALID, "run table entries must be in 32..1024");
+        if (value < 32 || value > 1024 || (value & 1)) return fail(c, GM2_ERR_INVALID, "run table entries must be even and in 32..1024");
         c->rt_cap = (int)value; return GM2_OK;
     default:
         return fail(c, GM2_ERR_INVALID, "gm2_configure: unknown key");
@@ -1300,7 +1345,7 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     p.rt_cap = c->rt_cap;
     p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
     p.prefix = c->prefix; p.debug = c->debug; p.order = c->order;
-    const size_t sm = 32 + (size_t)c->tile_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 8;
+    const size_t sm = 32 + (size_t)c->tile_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 24;
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
     // register budget follows the shared-memory footprint: small tiles -> 4+ CTAs/SM (64 regs),
     // large tiles -> 3 CTAs/SM (up to 85 regs)
