@@ -72,7 +72,7 @@ struct gm2_ctx {
     int packing = 1;
     uint8_t* d_seq = nullptr;
     int32_t *d_tile_slot = nullptr, *d_slot_src = nullptr, *d_slot_len = nullptr;
-    int2* d_slot_cov = nullptr; int32_t* d_cov_ovf = nullptr;
+    int2* d_slot_cov = nullptr; int32_t* d_cov_ovf = nullptr; int32_t* d_chunk_tile = nullptr;
 
     // name map
     int32_t V = 0;
@@ -183,7 +183,7 @@ __device__ __forceinline__ int ndigits_u64(unsigned long long v) {
 //   lookups; the row is assembled in shared memory with atomicOr and written out coalesced.
 // ------------------------------------------------------------------------------------------
 #define K1_WARPS 8
-__global__ void __launch_bounds__(K1_WARPS * 32)
+__global__ void __launch_bounds__(K1_WARPS * 32, 4)
 k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V, int32_t F,
                 const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
                 int FW, uint32_t* __restrict__ keep, int map_in_smem)
@@ -206,20 +206,26 @@ k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off
         for (int i = lane; i < FW; i += 32) row[i] = 0u;
         __syncwarp();
         const int64_t b = off[s], e = off[s + 1];
-        for (int64_t i0 = b; i0 < e; i0 += 128) {
-            int32_t id[4];
+        auto mark = [&](int32_t id) {
+            if ((uint32_t)id < (uint32_t)V)
+                for (int g = fg[id]; g >= 0; g = nx[g]) atomicOr(&row[g >> 5], 1u << (g & 31));
+        };
+        // head up to a 16-byte boundary, 128-bit body (two vectors per lane in flight), scalar tail
+        const int64_t b4 = min((b + 3) & ~(int64_t)3, e), e4 = b4 + ((e - b4) & ~(int64_t)3);
+        if (b + lane < b4) mark(__ldg(ids + b + lane));
+        const int4* v4 = reinterpret_cast<const int4*>(ids + b4);
+        const int64_t nv = (e4 - b4) >> 2;
+        for (int64_t i0 = 0; i0 < nv; i0 += 128) {
+            int4 x[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + lane + 32 * u;
-                id[u] = i < e ? __ldg(ids + i) : -1;
+                const int64_t i = i0 + 32 * u + lane;
+                x[u] = i < nv ? __ldg(v4 + i) : make_int4(-1, -1, -1, -1);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if ((uint32_t)id[u] < (uint32_t)V) {
-                    for (int g = fg[id[u]]; g >= 0; g = nx[g]) atomicOr(&row[g >> 5], 1u << (g & 31));
-                }
-            }
+            for (int u = 0; u < 4; ++u) { mark(x[u].x); mark(x[u].y); mark(x[u].z); mark(x[u].w); }
         }
+        if (e4 + lane < e) mark(__ldg(ids + e4 + lane));
         __syncwarp();
         uint32_t* dst = keep + (size_t)s * FW;
         for (int i = lane; i < FW; i += 32) dst[i] = row[i];
@@ -234,8 +240,9 @@ k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off
 //   slots are laid out per genome tile, each tile's slots padded to a multiple of 32 so that
 //   one ballot == one stored word and k_emit reads whole words.  Per slot the covering genes
 //   are inlined as a pair (x, y): -1 = none; y <= -2 points into an overflow list for the rare
-//   slot covered by more than two genes.  A warp reduces one tile at a time; warp 0 then scans
-//   the tile sums of each sample.
+//   slot covered by more than two genes.  A warp takes one tile at a time: branch-free bit tests,
+//   one ballot per 32 slots and sample, kept lengths accumulated in registers and reduced once per
+//   tile (REDUX); warp k then scans the tile sums of sample k.
 // ------------------------------------------------------------------------------------------
 #define PLAN_NS 4
 __device__ __forceinline__ bool keep_bit(const uint32_t* row, int g) {
@@ -252,7 +259,7 @@ k_plan(int64_t S, int FW, const uint32_t* __restrict__ keep, int ntiles,
 {
     extern __shared__ uint32_t plan_sm[];
     uint32_t* rows = plan_sm;                                   // PLAN_NS x FW
-    int32_t* tl = (int32_t*)(plan_sm + (size_t)PLAN_NS * FW);   // PLAN_NS x ntiles
+    int32_t* tl = (int32_t*)(plan_sm + (size_t)PLAN_NS * FW);   // PLAN_NS x ntiles kept lengths
     const int64_t sbase = (int64_t)blockIdx.x * PLAN_NS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
@@ -262,36 +269,59 @@ k_plan(int64_t S, int FW, const uint32_t* __restrict__ keep, int ntiles,
     }
     __syncthreads();
 
+    uint32_t* skw = (uint32_t*)(tl + PLAN_NS * ntiles);           // PLAN_NS x SW kept-bit words, staged
+
     for (int t = warp; t < ntiles; t += nwarps) {
-        const int sb = __ldg(tile_slot + t), se = __ldg(tile_slot + t + 1);   // multiples of 32
-        int sum[PLAN_NS];
+        const int c0 = __ldg(tile_slot + t) >> 5, c1 = __ldg(tile_slot + t + 1) >> 5;   // 32-slot chunks of the tile
+        int acc[PLAN_NS];
 #pragma unroll
-        for (int k = 0; k < PLAN_NS; ++k) sum[k] = 0;
-        for (int slot = sb + lane; slot < se; slot += 32) {
+        for (int k = 0; k < PLAN_NS; ++k) acc[k] = 0;
+        for (int c = c0; c < c1; ++c) {
+            const int slot = 32 * c + lane;
             const int len = __ldg(slot_len + slot);
             const int2 cv = __ldg(slot_cov + slot);
+            // branch-free bit tests: word/shift of both covering genes, computed once for all samples
+            const int gx = cv.x < 0 ? 0 : cv.x, gy = cv.y < 0 ? 0 : cv.y;
+            const int wx = gx >> 5, wy = gy >> 5;
+            const uint32_t sx = gx & 31, sy = gy & 31;
+            const uint32_t fx = cv.x < 0 ? 1u : 0u, fy = cv.y < 0 ? 1u : 0u;     // "no gene" counts as kept
+            const uint32_t live = len > 0 ? 1u : 0u;                            // padding slots have len 0
+            uint32_t kb[PLAN_NS];
 #pragma unroll
             for (int k = 0; k < PLAN_NS; ++k) {
-                const uint32_t* row = rows + (size_t)k * FW;
-                bool kept = len > 0 && keep_bit(row, cv.x);          // padding slots have len 0
-                if (kept) {
-                    if (cv.y >= -1) kept = keep_bit(row, cv.y);
-                    else {
-                        const int32_t* o = cov_ovf + (-cv.y - 2);
-                        const int n = __ldg(o);
-                        for (int j = 1; j <= n && kept; ++j) kept = keep_bit(row, __ldg(o + j));
+                const uint32_t* row = rows + k * FW;
+                kb[k] = live & ((row[wx] >> sx) | fx) & ((row[wy] >> sy) | fy) & 1u;
+            }
+            if (__any_sync(FULL_MASK, cv.y < -1)) {                             // rare: > 2 covering genes
+                if (cv.y < -1) {
+                    const int32_t* o = cov_ovf + (-cv.y - 2);
+                    const int n = __ldg(o);
+                    for (int j = 1; j <= n; ++j) {
+                        const int g = __ldg(o + j);
+#pragma unroll
+                        for (int k = 0; k < PLAN_NS; ++k) kb[k] &= (rows[k * FW + (g >> 5)] >> (g & 31)) & 1u;
                     }
                 }
-                const uint32_t w = __ballot_sync(FULL_MASK, kept);
-                if (lane == 0 && sbase + k < S) segkept[(size_t)(sbase + k) * SW + (slot >> 5)] = w;
-                sum[k] += kept ? len : 0;
+                __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < PLAN_NS; ++k) {
+                const uint32_t w = __ballot_sync(FULL_MASK, kb[k] != 0u);
+                if (lane == 0) skw[k * SW + c] = w;
+                acc[k] += kb[k] ? len : 0;
             }
         }
 #pragma unroll
         for (int k = 0; k < PLAN_NS; ++k) {
-            const int v = warp_sum(sum[k]);
+            const int v = __reduce_add_sync(FULL_MASK, acc[k]);
             if (lane == 0) tl[k * ntiles + t] = v;
         }
+    }
+    __syncthreads();
+    // kept-bit rows out, coalesced
+    for (int i = threadIdx.x; i < PLAN_NS * SW; i += blockDim.x) {
+        const int64_t s = sbase + i / SW;
+        if (s < S) segkept[(size_t)s * SW + (i % SW)] = skw[i];
     }
     __syncthreads();
     if (warp < PLAN_NS && sbase + warp < S) {
@@ -925,7 +955,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     if (!c) return GM2_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
+    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf, c->d_chunk_tile,
                      c->d_first_gene, c->d_next_same, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
                      c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
@@ -1107,6 +1137,12 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
     if ((rc = dev_upload(c, &c->d_slot_len, slot_len))) return rc;
     if ((rc = dev_upload(c, &c->d_slot_cov, slot_cov))) return rc;
     if ((rc = dev_upload(c, &c->d_cov_ovf, cov_ovf))) return rc;
+    {
+        std::vector<int32_t> chunk_tile(slot_src.size() / 32);
+        for (int t = 0; t < ntiles; ++t)
+            for (int32_t ch = tile_slot[t] / 32; ch < tile_slot[t + 1] / 32; ++ch) chunk_tile[(size_t)ch] = t;
+        if ((rc = dev_upload(c, &c->d_chunk_tile, chunk_tile))) return rc;
+    }
 
     c->G = G; c->F = F; c->FW = (F + 31) / 32;
     c->ntiles = ntiles; c->nseg = nseg; c->nslots = (int)slot_src.size(); c->SW = c->nslots / 32;
@@ -1176,6 +1212,7 @@ GM2_API int gm2_load_ids_dev(gm2_ctx* c, const int32_t* ids, const int64_t* off,
     int rc = begin_samples(c, S, "gm2_load_ids_dev"); if (rc) return rc;
     if (!c->d_first_gene) return fail(c, GM2_ERR_STATE, "gm2_load_ids_dev: call gm2_set_name_map first");
     if (!off || (n_ids > 0 && !ids) || n_ids < 0) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_dev: bad arguments");
+    if (((uintptr_t)ids & 15) || ((uintptr_t)off & 7)) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_dev: ids must be 16-byte aligned, off 8-byte aligned");
     c->ids = ids; c->ids_off = off; c->S = S; c->mode = 1;
     return GM2_OK;
 }
@@ -1239,7 +1276,7 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         }
     }
     if (S > 0) {
-        const size_t sm = ((size_t)c->FW + (size_t)c->ntiles) * 4 * PLAN_NS;
+        const size_t sm = ((size_t)c->FW + (size_t)c->ntiles + (size_t)c->SW) * 4 * PLAN_NS;
         if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: genome has too many genes/tiles for one CTA's shared memory");
         CU(c, cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         const int64_t blocks = (S + PLAN_NS - 1) / PLAN_NS;
