@@ -338,3 +338,52 @@ def test_many_genes_cover_one_segment():
         assert np.array_equal(ctx.lengths(), exp_len)
         assert exp_len[0] == G
         assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at full size (10,000 samples x K-12 shape, 26 GB image, device-resident):
+    every length against an independent numpy computation, structural bytes of every record,
+    64 records hashed on the device against the C oracle, idempotence of a second emit."""
+    import torch
+    g = synth.make_genome(seed=1)
+    starts, ends = g.starts_ends()
+    F = len(g.genes)
+    S = 10_000
+    keep = synth.random_keep_bool(F, S, 0.5, seed=2)
+    rows = synth.pack_keep_rows(keep)
+    # independent lengths: elementary segments, kept iff every covering gene is kept
+    bp = np.unique(np.concatenate([[0, g.G], starts, ends]))
+    seg_len = np.diff(bp)
+    removed_cover = np.zeros((S, len(seg_len)), dtype=bool)
+    for gi in range(F):
+        a, b = np.searchsorted(bp, starts[gi]), np.searchsorted(bp, ends[gi])
+        if b > a:
+            removed_cover[:, a:b] |= ~keep[:, gi:gi + 1]
+    exp_len = ((~removed_cover) * seg_len[None, :]).sum(1)
+    with _native.Context(0) as ctx:
+        ctx.set_reference(g.seq, starts, ends)
+        ctx.load_keep_host(rows)
+        ctx.plan(0)
+        assert np.array_equal(ctx.lengths(), exp_len)
+        off = ctx.record_offsets()
+        hdr = np.asarray([1 + len("Minimized_E_coli_K12_MG1655_") + len(str(i + 1)) + 1 for i in range(S)])
+        assert np.array_equal(np.diff(off), hdr + exp_len + 1)
+        img = torch.empty(int(off[-1]), dtype=torch.uint8, device="cuda:0")
+        ctx.emit_dev(0, S, img.data_ptr(), img.numel())
+        ctx.sync()
+        offs = torch.from_numpy(off).to("cuda:0")
+        assert bool((img[offs[:-1]] == ord(">")).all())                       # every record starts with '>'
+        assert bool((img[offs[1:] - 1] == 10).all())                          # ... and ends with '\n'
+        assert bool((img[offs[:-1] + torch.from_numpy(hdr).to("cuda:0") - 1] == 10).all())   # header newline
+        # exactly two newlines per record, no byte outside "ACGT" and the header alphabet elsewhere
+        assert int((img == 10).sum()) == 2 * S
+        pick = np.unique(np.linspace(0, S - 1, 64).astype(int))
+        got = ctx.diag_range_hashes(img.data_ptr(), img.numel(), off)
+        for s in pick:
+            _, h, _ = c_oracle.batch(g.seq, starts, ends, rows[s:s + 1], first_idx=int(s))
+            assert int(h[0]) == int(got[s]), s
+        # idempotence: a second emit into a fresh buffer gives the same hashes for every record
+        img.fill_(0)
+        ctx.emit_dev(0, S, img.data_ptr(), img.numel())
+        ctx.sync()
+        assert np.array_equal(ctx.diag_range_hashes(img.data_ptr(), img.numel(), off), got)
