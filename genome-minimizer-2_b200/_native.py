@@ -40,6 +40,9 @@ SIGNATURES = {
     "gm2_set_header_prefix": (_c.c_int, [_P, _c.c_char_p]),
     "gm2_load_ids_host": (_c.c_int, [_P, _P, _P, _I64]),
     "gm2_load_ids_dev": (_c.c_int, [_P, _P, _P, _I64, _I64]),
+    "gm2_set_forced": (_c.c_int, [_P, _P, _P]),
+    "gm2_load_probs_dev": (_c.c_int, [_P, _P, _I64, _I64, _c.c_float]),
+    "gm2_get_counts": (_c.c_int, [_P, _P]),
     "gm2_load_keep_host": (_c.c_int, [_P, _P, _I64]),
     "gm2_load_keep_dev": (_c.c_int, [_P, _P, _I64]),
     "gm2_plan": (_c.c_int, [_P, _I64]),
@@ -231,6 +234,20 @@ class Context:
     def load_keep_dev(self, rows_ptr: int, S: int):
         self._ck(self._lib.gm2_load_keep_dev(self._h, int(rows_ptr), int(S)))
         self.S = int(S)
+
+    def set_forced(self, force_keep_genes: Optional[np.ndarray], forced_ids: Optional[np.ndarray]):
+        fk = None if force_keep_genes is None else np.ascontiguousarray(force_keep_genes, dtype=np.uint32)
+        fi = None if forced_ids is None else np.ascontiguousarray(forced_ids, dtype=np.uint32)
+        self._ck(self._lib.gm2_set_forced(self._h, _ptr(fk), _ptr(fi)))
+
+    def load_probs_dev(self, probs_ptr: int, S: int, ld: int, threshold: float = 0.5):
+        self._ck(self._lib.gm2_load_probs_dev(self._h, int(probs_ptr), int(S), int(ld), float(threshold)))
+        self.S = int(S)
+
+    def counts(self) -> np.ndarray:
+        out = np.empty(self.S, dtype=np.int64)
+        self._ck(self._lib.gm2_get_counts(self._h, _ptr(out)))
+        return out
 
     # -- plan / results -------------------------------------------------------------------------
     def plan(self, first_idx: int = 0):

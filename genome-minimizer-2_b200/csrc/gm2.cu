@@ -77,10 +77,13 @@ struct gm2_ctx {
     // name map
     int32_t V = 0;
     int32_t *d_first_gene = nullptr, *d_next_same = nullptr;
+    uint32_t *d_forced_ids = nullptr, *d_force_keep = nullptr;     // optional (gm2_set_forced)
+    const float* probs = nullptr; int64_t probs_ld = 0; float probs_thr = 0.5f;   // mode 3 (borrowed)
+    int64_t* d_counts = nullptr; int64_t counts_cap = 0;
 
     // samples
     int64_t S = 0;
-    int mode = 0;                      // 0 none, 1 ids, 2 keep rows
+    int mode = 0;                      // 0 none, 1 ids, 2 keep rows, 3 dense probabilities
     const int32_t* ids = nullptr;      // device (owned or borrowed)
     const int64_t* ids_off = nullptr;
     const uint32_t* keep_in = nullptr; // device keep rows when mode == 2
@@ -231,6 +234,58 @@ k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off
         for (int i = lane; i < FW; i += 32) dst[i] = row[i];
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1'  keep-mask builder from dense probabilities (BASELINE config 5):
+//   the reference's  decode -> `> 0.5` (utils/extras.py:200-201) -> masks_to_gene_lists `>= 0.5`
+//   on the 0/1 matrix (explore_data/binary_converter.py:55,:64) -> check_essential_genes adds the
+//   missing essentials (:91-98) -> `name in needed` (minimizer_2.py:62), collapsed: column c is a
+//   name id; it is "present" iff probs[s][c] > threshold; a gene is kept iff its name's column is
+//   present or it is forced (essential).  counts[s] = length of the list the reference would
+//   have built = present columns + forced ids that are not present (+ a host-side constant for
+//   essentials that are no column at all).  One CTA per sample, coalesced 128-bit reads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_keep_from_probs(const float* __restrict__ probs, int64_t S, int64_t V, int64_t ld, float thr,
+                  const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
+                  const uint32_t* __restrict__ forced_ids, const uint32_t* __restrict__ force_keep,
+                  int FW, uint32_t* __restrict__ keep, int64_t* __restrict__ counts)
+{
+    extern __shared__ uint32_t kp_row[];
+    __shared__ int s_count;
+    const int64_t s = blockIdx.x;
+    for (int i = threadIdx.x; i < FW; i += blockDim.x) kp_row[i] = force_keep ? force_keep[i] : 0u;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const float* p = probs + s * ld;
+    int cnt = 0;
+    auto visit = [&](int64_t c, float v) {
+        if (v > thr) {
+            ++cnt;
+            for (int g = __ldg(first_gene + c); g >= 0; g = __ldg(next_same + g)) atomicOr(&kp_row[g >> 5], 1u << (g & 31));
+        } else if (forced_ids && ((__ldg(forced_ids + (c >> 5)) >> (c & 31)) & 1u)) {
+            ++cnt;                                   // an essential the reference appends to the list
+        }
+    };
+    int64_t head = (int64_t)(((16u - (uint32_t)((uintptr_t)p & 15u)) & 15u) >> 2);
+    if (head > V) head = V;
+    if (threadIdx.x < head) visit(threadIdx.x, __ldg(p + threadIdx.x));
+    const float4* v4 = reinterpret_cast<const float4*>(p + head);
+    const int64_t nvec = (V - head) >> 2;
+    for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const float4 v = __ldg(v4 + i);
+        const int64_t c = head + 4 * i;
+        visit(c, v.x); visit(c + 1, v.y); visit(c + 2, v.z); visit(c + 3, v.w);
+    }
+    const int64_t tail0 = head + 4 * nvec;
+    if (tail0 + threadIdx.x < V) visit(tail0 + threadIdx.x, __ldg(p + tail0 + threadIdx.x));
+    cnt = __reduce_add_sync(FULL_MASK, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
+    __syncthreads();
+    uint32_t* dst = keep + (size_t)s * FW;
+    for (int i = threadIdx.x; i < FW; i += blockDim.x) dst[i] = kp_row[i];
+    if (threadIdx.x == 0) counts[s] = s_count;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -956,7 +1011,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf, c->d_chunk_tile,
-                     c->d_first_gene, c->d_next_same, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
+                     c->d_first_gene, c->d_next_same, c->d_forced_ids, c->d_force_keep, c->d_counts, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
                      c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
     for (void* p : frees) if (p) cudaFree(p);
@@ -1178,6 +1233,8 @@ GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx,
     if ((rc = dev_upload(c, &c->d_first_gene, first))) return rc;
     if ((rc = dev_upload(c, &c->d_next_same, next))) return rc;
     c->V = V;
+    if (c->d_forced_ids) { cudaFree(c->d_forced_ids); c->d_forced_ids = nullptr; }
+    if (c->d_force_keep) { cudaFree(c->d_force_keep); c->d_force_keep = nullptr; }
     return GM2_OK;
 }
 
@@ -1214,6 +1271,46 @@ GM2_API int gm2_load_ids_dev(gm2_ctx* c, const int32_t* ids, const int64_t* off,
     if (!off || (n_ids > 0 && !ids) || n_ids < 0) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_dev: bad arguments");
     if (((uintptr_t)ids & 15) || ((uintptr_t)off & 7)) return fail(c, GM2_ERR_INVALID, "gm2_load_ids_dev: ids must be 16-byte aligned, off 8-byte aligned");
     c->ids = ids; c->ids_off = off; c->S = S; c->mode = 1;
+    return GM2_OK;
+}
+
+GM2_API int gm2_set_forced(gm2_ctx* c, const uint32_t* force_keep, const uint32_t* forced_ids) {
+    if (!c) return GM2_ERR_INVALID;
+    if (!c->d_first_gene) return fail(c, GM2_ERR_STATE, "gm2_set_forced: call gm2_set_name_map first");
+    CU(c, cudaSetDevice(c->device));
+    if (c->d_forced_ids) { cudaFree(c->d_forced_ids); c->d_forced_ids = nullptr; }
+    if (c->d_force_keep) { cudaFree(c->d_force_keep); c->d_force_keep = nullptr; }
+    int rc;
+    if (force_keep) {
+        std::vector<uint32_t> v(force_keep, force_keep + c->FW);
+        if (c->F & 31) { if (c->FW > 0) v[c->FW - 1] &= (1u << (c->F & 31)) - 1u; }     // bits beyond F stay clear
+        if ((rc = dev_upload(c, &c->d_force_keep, v))) return rc;
+    }
+    if (forced_ids) {
+        std::vector<uint32_t> v(forced_ids, forced_ids + (c->V + 31) / 32);
+        if ((rc = dev_upload(c, &c->d_forced_ids, v))) return rc;
+    }
+    c->planned = false; c->host_plan = false;
+    return GM2_OK;
+}
+
+GM2_API int gm2_load_probs_dev(gm2_ctx* c, const float* probs, int64_t S, int64_t ld, float threshold) {
+    int rc = begin_samples(c, S, "gm2_load_probs_dev"); if (rc) return rc;
+    if (!c->d_first_gene) return fail(c, GM2_ERR_STATE, "gm2_load_probs_dev: call gm2_set_name_map first (columns are name ids)");
+    if ((S > 0 && !probs) || ld < c->V || ((uintptr_t)probs & 3)) return fail(c, GM2_ERR_INVALID, "gm2_load_probs_dev: bad arguments (ld >= V, 4-byte aligned pointer)");
+    c->probs = probs; c->probs_ld = ld; c->probs_thr = threshold; c->S = S; c->mode = 3;
+    return GM2_OK;
+}
+
+GM2_API int gm2_get_counts(gm2_ctx* c, int64_t* out) {
+    if (!c) return GM2_ERR_INVALID;
+    if (!c->planned || c->mode != 3) return fail(c, GM2_ERR_STATE, "gm2_get_counts: needs a plan over gm2_load_probs_dev samples");
+    CU(c, cudaSetDevice(c->device));
+    if (c->S > 0) {
+        if (!out) return fail(c, GM2_ERR_INVALID, "gm2_get_counts: out is NULL");
+        CU(c, cudaMemcpyAsync(out, c->d_counts, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
     return GM2_OK;
 }
 
@@ -1257,6 +1354,19 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         c->rec_cap = S + 1;
     }
     const uint32_t* keep = c->keep_in;
+    if (c->mode == 3) {
+        if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;
+        if ((rc = dev_reserve(c, &c->d_counts, &c->counts_cap, S))) return rc;
+        keep = c->own_keep;
+        if (S > 0) {
+            const size_t sm = (size_t)std::max(c->FW, 1) * 4;
+            if (sm > 48 * 1024) CU(c, cudaFuncSetAttribute(k_keep_from_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_keep_from_probs<<<(unsigned)S, 256, sm, c->stream>>>(c->probs, S, c->V, c->probs_ld, c->probs_thr, c->d_first_gene,
+                                                                c->d_next_same, c->d_forced_ids, c->d_force_keep, c->FW,
+                                                                c->own_keep, c->d_counts);
+            LAUNCH_CHECK(c, "k_keep_from_probs");
+        }
+    }
     if (c->mode == 1) {
         if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;
         keep = c->own_keep;
@@ -1339,7 +1449,7 @@ GM2_API int gm2_get_keep_rows(gm2_ctx* c, uint32_t* out) {
     if (!c) return GM2_ERR_INVALID;
     if (!c->planned) return fail(c, GM2_ERR_STATE, "gm2_get_keep_rows: call gm2_plan first");
     CU(c, cudaSetDevice(c->device));
-    const uint32_t* keep = c->mode == 1 ? c->own_keep : c->keep_in;
+    const uint32_t* keep = c->mode == 2 ? c->keep_in : c->own_keep;
     const int64_t n = c->S * c->FW;
     if (n > 0) {
         if (!out) return fail(c, GM2_ERR_INVALID, "gm2_get_keep_rows: out is NULL");

@@ -328,3 +328,122 @@ def run_multi_file(record, all_lists, model_name: str, output_dir, filename_temp
         tot_red += _pct(G, int(lengths[idx]))
         tot_len += int(lengths[idx])
     return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}
+
+
+# ----------------------------------------------------------------------------------------------
+# VAE decoder output -> keep masks on the device (BASELINE config 5)
+# ----------------------------------------------------------------------------------------------
+class ColumnSpace:
+    """The mask columns of the reference's sample -> convert-samples -> minimizer chain, as name ids.
+
+    Reference semantics collapsed here (explore_data/binary_converter.py):
+      * duplicate column names: first occurrence kept, the rest dropped, and mask rows must then have
+        the de-duplicated length (:29-36, :50-53);
+      * a column is present iff its mask value >= 0.5 (:55), on the 0/1 matrix that `> 0.5` produced
+        (utils/extras.py:200-201);
+      * check_essential_genes adds every essential name that is missing (:91-98).
+    """
+
+    def __init__(self, table: GeneTable, col_names: Sequence[str], essential: Iterable[str] = ()):
+        seen: Dict[str, int] = {}
+        keep_first = []
+        for i, nm in enumerate(col_names):
+            nm = str(nm)
+            if nm not in seen:
+                seen[nm] = len(keep_first)
+                keep_first.append(nm)
+        self.cols: List[str] = keep_first
+        self.col_of: Dict[str, int] = seen
+        self.V = len(keep_first)
+        self.duplicates_dropped = len(col_names) - self.V
+        genes_of: Dict[str, List[int]] = {}
+        for g, nm in enumerate(table.names):
+            genes_of.setdefault(nm, []).append(g)
+        rows = [genes_of.get(nm, []) for nm in self.cols]
+        self.id2gene_off = np.zeros(self.V + 1, dtype=np.int32)
+        if rows:
+            self.id2gene_off[1:] = np.cumsum([len(r) for r in rows])
+        self.id2gene_idx = np.asarray([g for r in rows for g in r], dtype=np.int32)
+        ess = {str(e) for e in essential}
+        fw = (table.F + 31) // 32
+        fk = np.zeros(fw * 32, dtype=np.uint8)
+        for g, nm in enumerate(table.names):
+            if nm in ess:
+                fk[g] = 1
+        self.force_keep = np.packbits(fk, bitorder="little").view("<u4") if fw else np.zeros(0, dtype=np.uint32)
+        vw = (self.V + 31) // 32
+        fi = np.zeros(vw * 32, dtype=np.uint8)
+        for nm in ess:
+            c = seen.get(nm)
+            if c is not None:
+                fi[c] = 1
+        self.forced_ids = np.packbits(fi, bitorder="little").view("<u4") if vw else np.zeros(0, dtype=np.uint32)
+        self.essentials_not_in_columns = sum(1 for nm in ess if nm not in seen)
+
+
+def _device_matrix(probs) -> Tuple[int, int, int, int]:
+    """(pointer, S, V, row stride in elements) of a float32 CUDA matrix (torch tensor or anything
+    exposing data_ptr / shape / stride / dtype the same way)."""
+    if len(probs.shape) != 2:
+        raise ValueError("probabilities must be a 2-D [samples, columns] matrix")
+    if "float32" not in str(probs.dtype):
+        raise ValueError("probabilities must be float32")
+    if hasattr(probs, "is_cuda") and not probs.is_cuda:
+        raise ValueError("probabilities must live on the GPU (there is no CPU path)")
+    st = probs.stride()
+    if st[1] != 1:
+        raise ValueError("probabilities must be row-major with unit column stride")
+    return int(probs.data_ptr()), int(probs.shape[0]), int(probs.shape[1]), int(st[0])
+
+
+def plan_from_probabilities(eng: MinimizerEngine, space: ColumnSpace, probs, threshold: float = 0.5,
+                            first_idx: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Device-resident decoder output -> plan.  Returns (lengths, list lengths the reference would print)."""
+    ptr, S, V, ld = _device_matrix(probs)
+    if V != space.V:
+        # the reference raises here too (binary_converter.py:50-53)
+        raise ValueError(f"Mask row has length {V}, but dataset has {space.V} gene columns.")
+    eng.ctx.set_name_map(space.id2gene_off, space.id2gene_idx)
+    eng.ctx.set_forced(space.force_keep, space.forced_ids)
+    eng.ctx.load_probs_dev(ptr, S, ld, threshold)
+    eng.ctx.plan(first_idx)
+    eng.first_idx = first_idx
+    return eng.ctx.lengths(), eng.ctx.counts() + space.essentials_not_in_columns
+
+
+def run_single_file_from_probabilities(record, probs, col_names: Sequence[str], essential: Iterable[str],
+                                       model_name: str, output_file: str, threshold: float = 0.5,
+                                       engine: Optional[MinimizerEngine] = None) -> dict:
+    """The reference's three-step chain (`--mode sample` -> `--mode convert-samples` -> `--mode minimizer
+    --single-file`) for samples that are still on the GPU: same FASTA file, same progress lines, same
+    return dict as process_multiple_genomes_single_file on the `_with_essentials.npy` lists."""
+    G = len(record.seq)
+    eng = engine or MinimizerEngine(record)
+    try:
+        space = ColumnSpace(eng.table, col_names, essential)
+        lengths, counts = plan_from_probabilities(eng, space, probs, threshold)
+        n = len(lengths)
+        os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
+        with open(output_file, "wb") as out:
+            out.write((f"# Minimized genomes generated using model: {model_name}\n"
+                       f"# Total genomes: {n}\n"
+                       f"# Generated on: {np.datetime64('now')}\n").encode())
+
+            def sink(sa: int, sb: int, view: np.ndarray) -> None:
+                out.write(view)
+                for idx in range(sa, sb):
+                    print(f"[{idx+1}/{n}] genes present: {int(counts[idx])}")
+                    if _sampled(idx):
+                        L = int(lengths[idx])
+                        print(f"  → {L:,} bp ({_pct(G, L):.1f}% reduction)")
+
+            eng.drain(sink)
+    finally:
+        if engine is None:
+            eng.close()
+    tot_red, tot_len = 0.0, 0
+    for idx in range(n):
+        if _sampled(idx):
+            tot_red += _pct(G, int(lengths[idx]))
+            tot_len += int(lengths[idx])
+    return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}

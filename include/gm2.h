@@ -111,7 +111,20 @@ int gm2_load_ids_dev (gm2_ctx* ctx, const int32_t* ids, const int64_t* off /* S+
 int gm2_load_keep_host(gm2_ctx* ctx, const uint32_t* keep_rows, int64_t S);
 int gm2_load_keep_dev (gm2_ctx* ctx, const uint32_t* keep_rows, int64_t S);
 
-/* K1 keep-mask builder (ids mode only), K2 segment flags, K3 scans: replaces
+/* Dense form (BASELINE config 5): the samples are rows of a device-resident
+ * float32 matrix probs[S][ld] (the VAE decoder's output, utils/extras.py:192-203); column c is
+ * name id c of gm2_set_name_map; a column is present iff probs[s][c] > threshold (strict, as
+ * utils/extras.py:200-201; identical to binary_converter.py:55 on the resulting 0/1 matrix).
+ * gm2_set_forced registers genes that are always kept (the essentials check_essential_genes
+ * appends, binary_converter.py:91-98; one bit per gene, ceil(F/32) words) and, for the list
+ * length the reference prints, which ids are forced (one bit per id, ceil(V/32) words); either
+ * may be NULL.  The matrix is borrowed like the other *_dev inputs.  gm2_get_counts returns per
+ * sample (#ids above threshold) + (#forced ids not above threshold). */
+int gm2_set_forced(gm2_ctx* ctx, const uint32_t* force_keep_genes, const uint32_t* forced_ids);
+int gm2_load_probs_dev(gm2_ctx* ctx, const float* probs, int64_t S, int64_t ld, float threshold);
+int gm2_get_counts(gm2_ctx* ctx, int64_t* counts /* S */);
+
+/* K1 keep-mask builder (ids / dense modes), K2 segment flags, K3 scans: replaces
  * `_extract_non_essential_genes` (minimizer_2.py:50-66), `_get_positions_to_remove`
  * (:68-83) and the running output index of `_create_minimized_sequence` (:94-96).
  * `first_idx` is the global 0-based index of sample 0 (a rank's shard offset).

@@ -220,6 +220,50 @@ EDGE_LISTS = [["wrap", "fuzzy", "cjoin", "ordr", "single", "unquoted", "twin", "
               ["wrap", "unquoted"], ["wrap", "twin"], ["wrap", "unquoted", "twin", "fuzzy", "cjoin", "ordr", "single"]]
 
 
+def converter_cases(ref):
+    """The reference's own producer chain: thresholded decoder output -> masks_to_gene_lists ->
+    check_essential_genes (explore_data/binary_converter.py) -> minimizer."""
+    import importlib
+    import pandas as pd
+    bc = importlib.import_module("src.genome_minimizer_2.explore_data.binary_converter")
+    out = {}
+    for k, (G, F, seed, extra_cols, dup) in enumerate([(3000, 40, 41, 25, False), (5000, 70, 42, 60, True)]):
+        g = synth.make_genome(G, F, seed, nested=3, dup_name_frac=0.08, nameless_frac=0.05, name=f"CONV{k}")
+        text = synth.genbank_text(g, seed=seed)
+        rng = np.random.default_rng(seed)
+        gene_names = list(dict.fromkeys(n for n in g.gene_names() if n))
+        cols = gene_names[: int(len(gene_names) * 0.8)] + [f"group_{i}" for i in range(extra_cols)]
+        order = rng.permutation(len(cols))
+        cols = [cols[i] for i in order]
+        if dup:
+            cols = cols + [cols[3], cols[7]]                     # duplicate column names: first occurrence wins
+        P = len(dict.fromkeys(cols))
+        N = 9
+        decoded = rng.random((N, P)).astype(np.float32)
+        decoded[0, :] = 0.5                                      # exactly the threshold: not present (strict >)
+        decoded[1, :] = 0.0
+        decoded[2, :] = 1.0
+        decoded[3, ::2] = np.float32(0.50000006)                 # just above
+        binary = (decoded > 0.5).astype(float)                   # utils/extras.py:199-201
+        essential = set(gene_names[::7][:6]) | {gene_names[-1], "not_a_column_1", "not_a_column_2"}
+        with tempfile.TemporaryDirectory() as d:
+            masks_path = os.path.join(d, "binary.npy")
+            np.save(masks_path, binary)
+            ids_path = os.path.join(d, "ids.npy")
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                bc.masks_to_gene_lists(masks_path, pd.Index(cols), ids_path)
+                id_lists = np.load(ids_path, allow_pickle=True)
+                filled = bc.check_essential_genes(essential, id_lists, ids_path)
+            lists = np.load(ids_path, allow_pickle=True).tolist()
+            lists_ess = np.load(filled, allow_pickle=True).tolist()
+        case = run_reference(ref, text, lists_ess, f"conv{k}")
+        case.update({"columns": cols, "decoded": decoded.tolist(), "essential": sorted(essential),
+                     "lists_before_essentials": lists})
+        out[f"converter_{k}"] = case
+    return out
+
+
 def main():
     ref = import_reference()
     cases = {}
@@ -259,6 +303,8 @@ def main():
         fh.write(gb_text)
     big["genbank_file"] = "medium_k12.gb.gz"
     cases["medium_k12"] = big
+
+    cases.update(converter_cases(ref))
 
     for name, case in cases.items():
         with open(os.path.join(HERE, name + ".json"), "w") as fh:
