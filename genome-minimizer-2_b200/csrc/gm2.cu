@@ -72,7 +72,7 @@ struct gm2_ctx {
     int packing = 1;
     uint8_t* d_seq = nullptr;
     int32_t *d_tile_slot = nullptr, *d_slot_src = nullptr, *d_slot_len = nullptr;
-    int2* d_slot_cov = nullptr; int32_t* d_cov_ovf = nullptr; int32_t* d_chunk_tile = nullptr;
+    int2* d_slot_cov = nullptr; int32_t* d_cov_ovf = nullptr;
 
     // name map
     int32_t V = 0;
@@ -94,7 +94,8 @@ struct gm2_ctx {
     // plan outputs (device)
     uint32_t* d_segkept = nullptr; int64_t segkept_cap = 0;    // words
     int32_t* d_tile_off = nullptr; int64_t tile_off_cap = 0;   // elements
-    int64_t *d_len = nullptr, *d_rec_size = nullptr, *d_rec_off = nullptr; int64_t rec_cap = 0;
+    int64_t *d_len = nullptr, *d_rec_size = nullptr, *d_rec_off = nullptr;
+    int64_t len_cap = 0, rec_size_cap = 0, rec_off_cap = 0;
     unsigned long long* d_scan_desc = nullptr; int64_t scan_desc_cap = 0;
     unsigned int* d_scan_ticket = nullptr;
     // plan outputs (pinned host mirror)
@@ -1010,7 +1011,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     if (!c) return GM2_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf, c->d_chunk_tile,
+    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
                      c->d_first_gene, c->d_next_same, c->d_forced_ids, c->d_force_keep, c->d_counts, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
                      c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
@@ -1192,12 +1193,6 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
     if ((rc = dev_upload(c, &c->d_slot_len, slot_len))) return rc;
     if ((rc = dev_upload(c, &c->d_slot_cov, slot_cov))) return rc;
     if ((rc = dev_upload(c, &c->d_cov_ovf, cov_ovf))) return rc;
-    {
-        std::vector<int32_t> chunk_tile(slot_src.size() / 32);
-        for (int t = 0; t < ntiles; ++t)
-            for (int32_t ch = tile_slot[t] / 32; ch < tile_slot[t + 1] / 32; ++ch) chunk_tile[(size_t)ch] = t;
-        if ((rc = dev_upload(c, &c->d_chunk_tile, chunk_tile))) return rc;
-    }
 
     c->G = G; c->F = F; c->FW = (F + 31) / 32;
     c->ntiles = ntiles; c->nseg = nseg; c->nslots = (int)slot_src.size(); c->SW = c->nslots / 32;
@@ -1346,13 +1341,9 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
     int rc;
     if ((rc = dev_reserve(c, &c->d_segkept, &c->segkept_cap, S * c->SW))) return rc;
     if ((rc = dev_reserve(c, &c->d_tile_off, &c->tile_off_cap, S * (int64_t)c->ntiles))) return rc;
-    if (S + 1 > c->rec_cap || !c->d_len) {
-        int64_t dummy;
-        dummy = 0; if ((rc = dev_reserve(c, &c->d_len, &dummy, S + 1))) return rc;
-        dummy = 0; if ((rc = dev_reserve(c, &c->d_rec_size, &dummy, S + 1))) return rc;
-        dummy = 0; if ((rc = dev_reserve(c, &c->d_rec_off, &dummy, S + 1))) return rc;
-        c->rec_cap = S + 1;
-    }
+    if ((rc = dev_reserve(c, &c->d_len, &c->len_cap, S + 1))) return rc;
+    if ((rc = dev_reserve(c, &c->d_rec_size, &c->rec_size_cap, S + 1))) return rc;
+    if ((rc = dev_reserve(c, &c->d_rec_off, &c->rec_off_cap, S + 1))) return rc;
     const uint32_t* keep = c->keep_in;
     if (c->mode == 3) {
         if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;

@@ -35,6 +35,38 @@ def _default_dir() -> str:
     return os.path.join(PROJECT_ROOT, "minimized_genomes")
 
 
+# One resident engine per record object: the reference's loop builds a GenomeMinimiser per sample on a
+# shared record (minimizer_2.py:469-475); re-uploading the genome for each would dominate.
+_ENGINES: "dict[int, tuple]" = {}
+
+
+def _engine_for(record) -> _engine.MinimizerEngine:
+    import weakref
+    key = id(record)
+    sig = (len(record.seq), len(record.features))      # cheap staleness check for a record edited in place
+    hit = _ENGINES.get(key)
+    if hit is not None and hit[0]() is record and hit[2] == sig:
+        return hit[1]
+    if hit is not None:
+        _ENGINES.pop(key, None)
+        hit[1].close()
+    eng = _engine.MinimizerEngine(record)
+
+    def _drop(_ref, key=key):
+        old = _ENGINES.pop(key, None)
+        if old is not None:
+            try:
+                old[1].close()
+            except Exception:
+                pass
+
+    try:
+        _ENGINES[key] = (weakref.ref(record, _drop), eng, sig)
+    except TypeError:                       # record type without weakref support: no caching
+        _ENGINES.pop(key, None)
+    return eng
+
+
 class GenomeMinimiser:
     """One sample's minimization; attribute-compatible with the reference class.
 
@@ -59,12 +91,8 @@ class GenomeMinimiser:
         else:
             self.needed_genes = self.get_needed_genes(needed_genes_path)[idx]
 
-        eng = engine or _engine.MinimizerEngine(self.record)
-        try:
-            removed, self.reduced_genome_str = eng.minimize_one(self.needed_genes, idx)
-        finally:
-            if engine is None:
-                eng.close()
+        eng = engine or _engine_for(self.record)
+        removed, self.reduced_genome_str = eng.minimize_one(self.needed_genes, idx)
         self.features = [eng.table.features[g] for g in removed]                    # reference :50-66
         self._spans = [(int(eng.table.starts[g]), int(eng.table.ends[g])) for g in removed]
         self._positions: Optional[set] = None

@@ -390,3 +390,24 @@ def test_full_size_c2_properties():
         ctx.emit_dev(0, S, img.data_ptr(), img.numel())
         ctx.sync()
         assert np.array_equal(ctx.diag_range_hashes(img.data_ptr(), img.numel(), off), got)
+
+
+def test_class_facade_reuses_one_engine_per_record(golden_paths, golden):
+    """The reference builds one GenomeMinimiser per sample on a shared record; ours must not
+    re-upload the genome each time, and must still give every sample's exact sequence."""
+    import gc
+    from genome_minimizer_2_b200 import minimizer_2 as m2
+    gb, _ = golden_paths
+    rec = genbank.read_genbank(gb)
+    ref = genbank_reader.read_genbank(gb)
+    seqs = [m2.GenomeMinimiser(record=rec, needed_genes_list=l, idx=i).reduced_genome_str
+            for i, l in enumerate(golden["lists"][:6])]
+    assert id(rec) in m2._ENGINES and len([k for k in m2._ENGINES if k == id(rec)]) == 1
+    if "sequences" in golden:
+        assert seqs == golden["sequences"][:6]
+    else:
+        assert [len(s) for s in seqs] == golden["sequence_lengths"][:6]
+    key = id(rec)
+    del rec
+    gc.collect()
+    assert key not in m2._ENGINES                      # engine released with the record
