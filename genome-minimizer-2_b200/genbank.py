@@ -38,12 +38,33 @@ class Location:
 
 
 class Feature:
-    __slots__ = ("type", "location", "qualifiers")
+    """One feature-table entry.  `type` is parsed eagerly; `location` and `qualifiers` are parsed
+    from the entry's raw text on first access (the minimizer touches them for `gene` features only,
+    minimizer_2.py:59-61, :78-79 — a K-12 file has as many CDS entries that are never looked at)."""
+    __slots__ = ("type", "_raw", "_loc", "_quals", "__weakref__")
 
-    def __init__(self, type: str, location: Location, qualifiers: Dict[str, List[str]]):
+    def __init__(self, type: str, location: "Location | None" = None, qualifiers: "Dict[str, List[str]] | None" = None,
+                 raw: "str | None" = None):
         self.type = type
-        self.location = location
-        self.qualifiers = qualifiers
+        self._raw = raw
+        self._loc = location
+        self._quals = qualifiers
+
+    def _parse(self) -> None:
+        loc, quals = _parse_feature_body(self._raw)
+        self._loc, self._quals, self._raw = loc, quals, None
+
+    @property
+    def location(self) -> Location:
+        if self._raw is not None:
+            self._parse()
+        return self._loc
+
+    @property
+    def qualifiers(self) -> Dict[str, List[str]]:
+        if self._raw is not None:
+            self._parse()
+        return self._quals
 
     def __repr__(self):
         return f"Feature({self.type!r}, {self.location!r})"
@@ -106,58 +127,71 @@ def _unquote(key: str, value: str) -> str:
     return value
 
 
-def _parse_features(lines: List[str]) -> List[Feature]:
-    # group the block into one chunk of lines per feature
-    chunks: List[List[str]] = []
-    for ln in lines:
-        if not ln.strip():
+_FEATURE_START = re.compile(r"^ {5}(?=\S)", re.M)
+_SIMPLE_LOC = re.compile(r"^(complement\()?(\d+)\.\.(\d+)\)?$")
+
+
+def _parse_feature_body(raw: str) -> Tuple[Location, Dict[str, List[str]]]:
+    """Location and qualifiers of one feature entry (its lines, key line first)."""
+    ch = [ln for ln in raw.split("\n") if ln.strip()]
+    loc_parts = [ch[0][21:].strip()]
+    i = 1
+    while i < len(ch) and not ch[i][21:].lstrip().startswith("/") and not ch[i].lstrip().startswith("/"):
+        loc_parts.append(ch[i].strip())
+        i += 1
+    quals: Dict[str, List[str]] = {}
+    while i < len(ch):
+        body = ch[i][21:] if ch[i][:21].strip() == "" else ch[i].strip()
+        i += 1
+        if not body.startswith("/"):
+            continue                                   # stray continuation: ignore
+        if "=" not in body:
+            quals.setdefault(body[1:].strip(), [""])    # bare /key (only if not seen yet)
             continue
-        if ln.startswith("     ") and len(ln) > 5 and ln[5] != " ":
-            chunks.append([ln])
-        elif chunks:
-            chunks[-1].append(ln)
+        qk, qv = body[1:].split("=", 1)
+        if qv.startswith('"'):
+            pieces = [qv]
+            while (pieces[-1] == '"' and len(pieces) == 1 or not pieces[-1].endswith('"')) and i < len(ch):
+                nxt = ch[i][21:] if ch[i][:21].strip() == "" else ch[i].strip()
+                pieces.append(nxt.strip())
+                i += 1
+            qv = " ".join(pieces)
+        quals.setdefault(qk, []).append(_unquote(qk, qv))
+    text = "".join(loc_parts)
+    m = _SIMPLE_LOC.match(text)
+    if m and (m.group(1) is None) == (not text.endswith(")")):
+        loc = Location(int(m.group(2)) - 1, int(m.group(3)), -1 if m.group(1) else 1)
+    else:
+        loc = parse_location(text)
+    return loc, quals
+
+
+def _parse_features(block: str) -> List[Feature]:
+    """Feature table text (between the FEATURES line and the next column-0 keyword) -> features.
+    One regex pass finds the entries (5 blanks, then the key in columns 6-20); bodies stay raw."""
+    starts = [m.start() for m in _FEATURE_START.finditer(block)]
+    starts.append(len(block))
     feats: List[Feature] = []
-    for ch in chunks:
-        key = ch[0][5:21].strip()
-        loc_parts = [ch[0][21:].strip()]
-        i = 1
-        while i < len(ch) and not ch[i][21:].lstrip().startswith("/") and not ch[i].lstrip().startswith("/"):
-            loc_parts.append(ch[i].strip())
-            i += 1
-        quals: Dict[str, List[str]] = {}
-        while i < len(ch):
-            body = ch[i][21:] if ch[i][:21].strip() == "" else ch[i].strip()
-            i += 1
-            if not body.startswith("/"):
-                continue                                   # stray continuation: ignore
-            if "=" not in body:
-                quals.setdefault(body[1:].strip(), [""])    # bare /key (only if not seen yet)
-                continue
-            qk, qv = body[1:].split("=", 1)
-            if qv.startswith('"'):
-                pieces = [qv]
-                while (pieces[-1] == '"' and len(pieces) == 1 or not pieces[-1].endswith('"')) and i < len(ch):
-                    nxt = ch[i][21:] if ch[i][:21].strip() == "" else ch[i].strip()
-                    pieces.append(nxt.strip())
-                    i += 1
-                qv = " ".join(pieces)
-            quals.setdefault(qk, []).append(_unquote(qk, qv))
-        feats.append(Feature(key, parse_location("".join(loc_parts)), quals))
+    for a, b in zip(starts, starts[1:]):
+        raw = block[a:b]
+        feats.append(Feature(raw[5:21].split(None, 1)[0] if raw[5:21].strip() else "", raw=raw))
     return feats
 
 
 def _split_records(text: str) -> List[str]:
     recs: List[str] = []
-    pos = 0
-    while True:
-        m = re.compile(r"^LOCUS", re.M).search(text, pos)
-        if not m:
-            break
-        end = re.compile(r"^//", re.M).search(text, m.start())
-        stop = len(text) if not end else end.end()
-        recs.append(text[m.start():stop])
-        pos = stop
+    pos = 0 if text.startswith("LOCUS") else text.find("\nLOCUS")
+    while pos >= 0:
+        if text[pos] == "\n":
+            pos += 1
+        end = 0 if text.startswith("//", pos) else text.find("\n//", pos)
+        stop = len(text) if end < 0 else (text.find("\n", end + 1) + 1 or len(text))
+        recs.append(text[pos:stop])
+        pos = text.find("\nLOCUS", stop - 1)
     return recs
+
+
+_COL0_KEYWORD = re.compile(r"^\S", re.M)
 
 
 def read_genbank(path: str) -> GenomeRecord:
@@ -171,34 +205,21 @@ def read_genbank(path: str) -> GenomeRecord:
     if len(recs) > 1:
         raise ValueError("More than one record found in handle")
     rec = recs[0]
-    lines = rec.split("\n")
-    name = ""
-    first = lines[0].split()
-    if len(first) > 1:
-        name = first[1]
-    # locate blocks by their column-0 keywords
-    feat_lo = feat_hi = org_lo = None
-    for i, ln in enumerate(lines):
-        if feat_lo is None and ln.startswith("FEATURES"):
-            feat_lo = i + 1
-        elif feat_lo is not None and feat_hi is None and ln[:1] not in (" ", "") and not ln.startswith("FEATURES"):
-            feat_hi = i
-        if ln.startswith("ORIGIN"):
-            org_lo = i + 1
-            if feat_lo is not None and feat_hi is None:
-                feat_hi = i
-            break
+    first = rec[:rec.find("\n")].split() if "\n" in rec else rec.split()
+    name = first[1] if len(first) > 1 else ""
     feats: List[Feature] = []
-    if feat_lo is not None:
-        feats = _parse_features(lines[feat_lo:feat_hi if feat_hi is not None else len(lines)])
+    f0 = 0 if rec.startswith("FEATURES") else rec.find("\nFEATURES")
+    if f0 >= 0:
+        body0 = rec.find("\n", f0 + 1) + 1                     # first line after the FEATURES header
+        m = _COL0_KEYWORD.search(rec, body0) if body0 > 0 else None
+        feats = _parse_features(rec[body0:m.start() if m else len(rec)]) if body0 > 0 else []
     seq = ""
-    if org_lo is not None:
-        body = []
-        for ln in lines[org_lo:]:
-            if ln.startswith("//"):
-                break
-            body.append(ln[10:])
-        seq = "".join(body).replace(" ", "").replace("\r", "").upper()
+    o0 = rec.find("\nORIGIN")
+    if o0 >= 0:
+        body0 = rec.find("\n", o0 + 1) + 1
+        end = rec.find("\n//", body0 - 1)
+        block = rec[body0:end if end >= 0 else len(rec)] if body0 > 0 else ""
+        seq = "".join([ln[10:] for ln in block.split("\n")]).replace(" ", "").replace("\r", "").upper()
     return GenomeRecord(seq, feats, name=name)
 
 
