@@ -520,8 +520,8 @@ struct EmitParams {
     int rt_cap;            // run-table entries per warp (shared memory)
     int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
     int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
-    int debug;             // timing experiments only (wrong output): 1 no phase B, 2 no phase A stores,
-                           // 4 phase A stores without shared loads, 8 build the run table once per warp
+    int debug;             // timing experiments only (wrong output; needs -DGM2_EMIT_DEBUG): 1 no boundary
+                           // sectors, 2 no interior stores, 4 interior stores without shared loads
     HeaderPrefix prefix;
 };
 
@@ -662,10 +662,9 @@ __device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32
     }
     __syncwarp();
     // ---- the stream
-    int4 t = rtb_load(rtb_a);
     int dA = 0;
     for (int r = 0; r <= nr; ++r) {
-        const int4 tn = rtb_load(rtb_a + 16 * (r < nr ? r + 1 : nr));        // prefetch
+        const int4 t = rtb_load(rtb_a + 16 * r);                               // warp-uniform (broadcast)
         const int dB = t.z - t.x;                                            // S_r - Q_r
 #ifdef GM2_EMIT_DEBUG
         if ((t.y & RUN_HAS_BOUNDARY) && !(debug & 1)) {
@@ -714,7 +713,6 @@ __device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32
             }
         }
         dA = dB;
-        t = tn;
     }
     __syncwarp();
 }
@@ -793,7 +791,6 @@ k_emit(const EmitParams p)
             m_words = lane < nwords ? __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + lane) : 0u;
         }
     };
-    int dbg_nr = 0, dbg_q = 0;
     int64_t s = sb + warp;
     if (s < se) load_meta(s);
     while (s < se) {
@@ -818,17 +815,19 @@ k_emit(const EmitParams p)
         if (have_tile) {
             const int A = (int)((uintptr_t)seqout & 31u);
             uint8_t* base32 = seqout - A;
+            asm volatile("" : "+l"(base32));                   // keep the 64-bit base in registers (no re-derivation per run)
             int q = toff + A;
             int nr = 0;
             uint32_t carry = 0u;
-            if ((p.debug & 8) && s != sb + warp) {           // timing experiment: reuse the first sample's table
-                nr = dbg_nr; q = dbg_q;
-            } else
-            for (int c = 0; c < nwords; ++c) {
-                if (nr + 17 > p.rt_cap) {                       // table full: flush what we have
-                    if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                    emit_runs<POLICY>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
-                    nr = 0; carry = 0u;
+            for (int c = 0; ; ++c) {
+                const bool done = c >= nwords;
+                if (done || nr + 17 > p.rt_cap) {               // tile finished, or table full: emit what we have
+                    if (nr > 0) {
+                        if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
+                        emit_runs<POLICY>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
+                        nr = 0; carry = 0u;
+                    }
+                    if (done) break;
                 }
                 const uint32_t w = c < 32 ? __shfl_sync(FULL_MASK, words, c)
                                           : __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + c);   // warp-uniform
@@ -842,11 +841,6 @@ k_emit(const EmitParams p)
                 if ((starts >> lane) & 1u) rt_store(rt_a + 8u * (nr + __popc(starts & lt_mask)), q + incl - x, src);
                 nr += __popc(starts);
                 q += __shfl_sync(FULL_MASK, incl, 31);
-            }
-            if (p.debug & 8) { dbg_nr = nr; dbg_q = q; }
-            if (nr > 0) {
-                if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                emit_runs<POLICY>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
             }
         }
         if (tile == last_tile && lane == 0) seqout[__ldg(p.lengths + s)] = (uint8_t)'\n';
