@@ -53,6 +53,7 @@ SIGNATURES = {
     "gm2_image_bytes": (_c.c_int, [_P, _I64, _I64, _c.POINTER(_I64)]),
     "gm2_emit_dev": (_c.c_int, [_P, _I64, _I64, _P, _I64]),
     "gm2_emit_host": (_c.c_int, [_P, _I64, _I64, _P, _I64, _I64]),
+    "gm2_sequence_hashes": (_c.c_int, [_P, _I64, _I64, _P]),
     "gm2_minimize_host": (_c.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64]),
     "gm2_host_alloc": (_c.c_int, [_c.POINTER(_P), _I64]),
     "gm2_host_free": (_c.c_int, [_P]),
@@ -306,6 +307,12 @@ class Context:
                                               _ptr(lengths), _ptr(rec_off), _ptr(arr), arr.size, int(chunk_bytes)))
         self.S = int(S)
         return lengths, rec_off
+
+    def sequence_hashes(self, s0: int = 0, s1: Optional[int] = None) -> np.ndarray:
+        s1 = self.S if s1 is None else s1
+        out = np.zeros(s1 - s0, dtype=np.uint64)
+        self._ck(self._lib.gm2_sequence_hashes(self._h, int(s0), int(s1), _ptr(out)))
+        return out
 
     # -- diagnostics ------------------------------------------------------------------------------
     def diag_fill(self, dev_ptr: int, nbytes: int, pattern: int = 0x41414141):

@@ -898,12 +898,9 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
     return z ^ (z >> 31);
 }
 
-__global__ void __launch_bounds__(256)
-k_range_hashes(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t* __restrict__ off,
-               unsigned long long* __restrict__ out)
+__device__ __forceinline__ void range_hash_block(const uint8_t* __restrict__ buf, int64_t buf_bytes, int64_t o0, int64_t n,
+                                                 unsigned long long* __restrict__ out_r)
 {
-    const int64_t r = blockIdx.x;
-    const int64_t o0 = off[r], n = off[r + 1] - o0;
     const int64_t nwords = (n + 7) >> 3;
     const int m = (int)(o0 & 7);
     const uint8_t* abase = buf + (o0 - m);                       // 8-byte aligned (buf is)
@@ -935,9 +932,27 @@ k_range_hashes(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
         for (int i = 0; i < 8; ++i) t += part[i];
-        atomicAdd(out + r, t);
+        atomicAdd(out_r, t);
     }
 }
+
+__global__ void __launch_bounds__(256)
+k_range_hashes(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t* __restrict__ off,
+               unsigned long long* __restrict__ out)
+{
+    const int64_t r = blockIdx.x;
+    range_hash_block(buf, buf_bytes, off[r], off[r + 1] - off[r], out + r);
+}
+
+// same, ranges given as (begin, end) pairs
+__global__ void __launch_bounds__(256)
+k_range_hashes_pairs(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t* __restrict__ pairs,
+                     unsigned long long* __restrict__ out)
+{
+    const int64_t r = blockIdx.x;
+    range_hash_block(buf, buf_bytes, pairs[2 * r], pairs[2 * r + 1] - pairs[2 * r], out + r);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // C-ABI
@@ -1577,6 +1592,57 @@ GM2_API int gm2_diag_fill(gm2_ctx* c, uint8_t* dev, int64_t bytes, uint32_t patt
     const int blocks = c->sm_count * 16;
     k_fill<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<uint4*>(dev), nvec, pattern);
     LAUNCH_CHECK(c, "k_fill");
+    return GM2_OK;
+}
+
+// Hashes of the minimized SEQUENCES (bases only, no header / newline) of records [s0,s1), computed
+// on the device from staged emits: backs the reference's duplicate report
+// (check_sequence_duplicates, minimizer_2.py:273-303) without moving any base to the host.
+GM2_API int gm2_sequence_hashes(gm2_ctx* c, int64_t s0, int64_t s1, uint64_t* out) {
+    if (!c) return GM2_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    int rc = pull_plan(c); if (rc) return rc;
+    if (s0 < 0 || s1 < s0 || s1 > c->S) return fail(c, GM2_ERR_INVALID, "gm2_sequence_hashes: bad sample range");
+    if (s1 > s0 && !out) return fail(c, GM2_ERR_INVALID, "gm2_sequence_hashes: out is NULL");
+    const int64_t chunk = (int64_t)1 << 30;
+    int64_t need = 0;
+    for (int64_t s = s0; s < s1; ++s) need = std::max(need, c->h_rec_off[s + 1] - c->h_rec_off[s]);
+    need = std::max(need, std::min(chunk, c->h_rec_off[s1] - c->h_rec_off[s0]));
+    need = (need + 7) & ~(int64_t)7;
+    if (need > c->stage_cap) {
+        for (int i = 0; i < 2; ++i) { if (c->d_stage[i]) cudaFree(c->d_stage[i]); c->d_stage[i] = nullptr; }
+        c->stage_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(c, cudaMalloc((void**)&c->d_stage[i], (size_t)need));
+        c->stage_cap = need;
+    }
+    int64_t a = s0;
+    while (a < s1) {
+        int64_t b = a + 1;
+        while (b < s1 && c->h_rec_off[b + 1] - c->h_rec_off[a] <= c->stage_cap) ++b;
+        if ((rc = launch_emit(c, a, b, c->d_stage[0]))) return rc;
+        // sequence of record s = [rec start + header, rec end - 1); header = record size - L - 1
+        const int64_t n = b - a;
+        int64_t* d_off = nullptr; unsigned long long* d_out = nullptr;
+        std::vector<int64_t> ranges((size_t)n * 2);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t r1 = c->h_rec_off[a + i + 1] - c->h_rec_off[a];
+            ranges[(size_t)(2 * i)] = r1 - 1 - c->h_len[a + i];
+            ranges[(size_t)(2 * i + 1)] = r1 - 1;
+        }
+        CU(c, cudaMalloc((void**)&d_off, (size_t)n * 16));
+        cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * 8);
+        if (e != cudaSuccess) { cudaFree(d_off); return cuda_fail(c, e, "cudaMalloc"); }
+        cudaMemcpyAsync(d_off, ranges.data(), (size_t)n * 16, cudaMemcpyHostToDevice, c->stream);
+        cudaMemsetAsync(d_out, 0, (size_t)n * 8, c->stream);
+        dim3 grid((unsigned)n, 32, 1);
+        k_range_hashes_pairs<<<grid, 256, 0, c->stream>>>(c->d_stage[0], c->stage_cap, d_off, d_out);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) { c->launches++; e = cudaMemcpyAsync(out + (a - s0), d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_off); cudaFree(d_out);
+        if (e != cudaSuccess) return cuda_fail(c, e, "gm2_sequence_hashes");
+        a = b;
+    }
     return GM2_OK;
 }
 

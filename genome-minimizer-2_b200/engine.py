@@ -186,6 +186,28 @@ class MinimizerEngine:
         kept = np.unpackbits(row.view(np.uint8), bitorder="little")[:self.table.F].astype(bool)
         return np.flatnonzero(~kept), self.sequence(0)
 
+    def duplicate_stats(self) -> dict:
+        """The reference's `check_sequence_duplicates` (minimizer_2.py:273-303) over the planned samples,
+        from device-side sequence hashes: sequences are grouped by (length, 64-bit hash) instead of by
+        the strings themselves; `duplicates_detail` maps a representative id to the ids of its group
+        (the reference keys it by the sequence string, which never leaves the GPU here)."""
+        n = self.S
+        lengths = self.ctx.lengths()
+        hashes = self.ctx.sequence_hashes(0, n)
+        groups: Dict[Tuple[int, int], List[str]] = {}
+        for s in range(n):
+            groups.setdefault((int(lengths[s]), int(hashes[s])), []).append(f"{SEQ_ID_PREFIX}{self.first_idx + s + 1}")
+        dup = {ids[0]: ids for ids in groups.values() if len(ids) > 1}
+        return {
+            "total_sequences": n,
+            "unique_sequences": len(groups),
+            "duplicate_groups": len(dup),
+            "duplicated_sequences": sum(len(v) for v in dup.values()),
+            "unique_only_sequences": sum(1 for v in groups.values() if len(v) == 1),
+            "duplicates_detail": dup,
+            "compression_ratio": len(groups) / n if n else 0,
+        }
+
     def _pin(self, i: int, nbytes: int) -> _native.PinnedBuffer:
         b = self._pinned[i]
         if b is None or b.nbytes < nbytes:

@@ -157,6 +157,12 @@ int gm2_emit_dev(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* dev_out, int64_t
 int gm2_emit_host(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* host_out, int64_t cap,
                   int64_t chunk_bytes);
 
+/* 64-bit hashes (definition: gm2_diag_range_hashes) of the minimized SEQUENCES of records [s0,s1)
+ * — bases only, header and newline excluded — computed on the device from staged emits.  Backs the
+ * reference's duplicate report (check_sequence_duplicates, minimizer_2.py:273-303): equal sequences
+ * have equal (length, hash).  `out` is a host array of s1-s0 values. */
+int gm2_sequence_hashes(gm2_ctx* ctx, int64_t s0, int64_t s1, uint64_t* out);
+
 /* One-call convenience used by the batch entry functions: load keep rows or ids from
  * host memory, plan, and deliver the whole image to host memory. */
 int gm2_minimize_host(gm2_ctx* ctx, const int32_t* ids, const int64_t* off,

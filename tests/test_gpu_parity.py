@@ -411,3 +411,52 @@ def test_class_facade_reuses_one_engine_per_record(golden_paths, golden):
     del rec
     gc.collect()
     assert key not in m2._ENGINES                      # engine released with the record
+
+
+def test_duplicate_stats_match_the_reference_definition():
+    """Device-side sequence hashes reproduce check_sequence_duplicates' numbers (minimizer_2.py:273-303)."""
+    g = synth.make_genome(60_000, 40, 61, nested=2)
+    starts, ends = g.starts_ends()
+    table = engine.GeneTable(g.gene_names(), starts, ends)
+    base = synth.make_gene_lists(g, 7, 0.5, seed=9, extra_names=3)
+    lists = base + [base[0], base[3], list(reversed(base[0])), base[0] + ["unknown_name"], [], []]
+    eng = engine.MinimizerEngine(seq=g.seq, table=table)
+    try:
+        eng.plan_lists(lists)
+        st = eng.duplicate_stats()
+        # reference definition on the actual strings (oracle)
+        seqs = {}
+        for i, l in enumerate(lists):
+            keep = mo.keep_vector(table.names, l)
+            seqs[f"id{i}"] = mo.minimize_numpy(g.seq, starts, ends, keep).tobytes()
+        from collections import defaultdict
+        grp = defaultdict(list)
+        for k, v in seqs.items():
+            grp[v].append(k)
+        dups = {k: v for k, v in grp.items() if len(v) > 1}
+        assert st["total_sequences"] == len(lists)
+        assert st["unique_sequences"] == len(grp)
+        assert st["duplicate_groups"] == len(dups)
+        assert st["duplicated_sequences"] == sum(len(v) for v in dups.values())
+        assert st["unique_only_sequences"] == sum(1 for v in grp.values() if len(v) == 1)
+        assert st["compression_ratio"] == len(grp) / len(lists)
+        # hashes are those of the bare sequences
+        h = eng.ctx.sequence_hashes()
+        assert [int(x) for x in h] == [mo.range_hash(v) for v in seqs.values()]
+    finally:
+        eng.close()
+
+
+def test_huge_record_ids_render_all_digits():
+    """Headers with 12-19 digit ids (a shard far into a huge job); ids cross a power of ten in the batch."""
+    g = synth.make_genome(9_000, 12, 71, nested=1)
+    starts, ends = g.starts_ends()
+    S = 25
+    rows = synth.pack_keep_rows(synth.random_keep_bool(len(g.genes), S, 0.5, seed=7))
+    for first in (999_999_999_990, 9_223_372_036_854_775_000):
+        exp_len, _, exp_img = _oracle_image(g.seq, starts, ends, rows, first_idx=first)
+        with _native.Context(0) as ctx:
+            ctx.set_reference(g.seq, starts, ends)
+            ctx.load_keep_host(rows)
+            ctx.plan(first)
+            assert np.array_equal(_gpu_image(ctx, S), exp_img)
