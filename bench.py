@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--emit-warps", type=int, default=0)
     ap.add_argument("--emit-batch", type=int, default=-1)
     ap.add_argument("--store-policy", type=int, default=-1)
+    ap.add_argument("--packing", type=int, default=0)
     ap.add_argument("--emit-order", type=int, default=-1)
     ap.add_argument("--emit-debug", type=int, default=0, help="timing experiments only (wrong output)")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -314,6 +315,8 @@ def main():
     ctx = _native.Context(local_rank)
     if args.tile_bytes:
         ctx.configure(_native.CFG_TILE_BYTES, args.tile_bytes)
+    if args.packing:
+        ctx.configure(_native.CFG_PACKING, args.packing)
     if args.emit_warps:
         ctx.configure(_native.CFG_EMIT_WARPS, args.emit_warps)
     if args.emit_batch >= 0:

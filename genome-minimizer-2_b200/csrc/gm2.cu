@@ -71,6 +71,7 @@ struct gm2_ctx {
     int ntiles = 0, nseg = 0, nslots = 0, SW = 0, max_tile_slots = 0;
     int packing = 1;
     uint8_t* d_seq = nullptr;
+    uint8_t* d_seq2 = nullptr;         // 2 bits per base (only when packing == 2)
     int32_t *d_tile_slot = nullptr, *d_slot_src = nullptr, *d_slot_len = nullptr;
     int2* d_slot_cov = nullptr; int32_t* d_cov_ovf = nullptr;
 
@@ -517,6 +518,7 @@ struct EmitParams {
     int64_t s0, s1;
     int64_t first_idx;
     int tile_bytes, ntiles, SW, batch, nbatch;
+    int tile_smem_bytes;   // bytes of the staged tile: tile_bytes (1 byte/base) or tile_bytes/4 (2 bits/base)
     int rt_cap;            // run-table entries per warp (shared memory)
     int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
     int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
@@ -575,6 +577,26 @@ __device__ __forceinline__ void st8(uint8_t* p, uint32_t v) {
 __device__ __forceinline__ void st256(uint8_t* p, const uint4& a, const uint4& b) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// ---- 2-bit packing (ACGT-only references): base i of the tile sits in bits [2i, 2i+2) of the
+// little-endian bit stream, code 0..3 = A, C, G, T.  Sixteen bases = one 32-bit word.
+#define ACGT_LUT 0x54474341u                     // 'A' 'C' 'G' 'T' as bytes 0..3
+__device__ __forceinline__ uint32_t spread8(uint32_t t) {      // 8 two-bit codes -> 8 nibbles
+    t &= 0xffffu;
+    t = (t | (t << 8)) & 0x00ff00ffu;
+    t = (t | (t << 4)) & 0x0f0f0f0fu;
+    t = (t | (t << 2)) & 0x33333333u;
+    return t;
+}
+__device__ __forceinline__ uint4 expand16(uint32_t x) {       // 16 codes -> 16 ASCII bytes (PRMT as a 4-entry LUT)
+    const uint32_t lo = spread8(x), hi = spread8(x >> 16);
+    return make_uint4(__byte_perm(ACGT_LUT, 0u, lo), __byte_perm(ACGT_LUT, 0u, lo >> 16),
+                      __byte_perm(ACGT_LUT, 0u, hi), __byte_perm(ACGT_LUT, 0u, hi >> 16));
+}
+__device__ __forceinline__ uint32_t base_at_2bit(uint32_t tile_a, int b) {
+    const uint32_t w = lds32(tile_a + (uint32_t)((b >> 4) << 2));
+    return (ACGT_LUT >> (8u * ((w >> (2 * (b & 15))) & 3u))) & 0xffu;
 }
 
 // Interior of one kept run: nb destination-aligned 16-byte vectors, lanes strided by 32.
@@ -639,7 +661,7 @@ __device__ __forceinline__ void rtb_store(uint32_t a, int x, int y, int z, int w
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-template <int POLICY>
+template <int POLICY, int PACK>
 __device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32_t rtb_a, int nr,
                                           uint8_t* __restrict__ base32, int lane, int debug)
 {
@@ -683,11 +705,21 @@ __device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32
                            while (pos >= qn) { ++rr; ec = rt_load(rt_a + 8 * rr); qn = rt_load(rt_a + 8 * (rr + 1)).x; } }
                     src = ec.y + (pos - ec.x);
                 }
-                st8<POLICY>(base32 + pos, lds8(tile_a + (uint32_t)src));
+                st8<POLICY>(base32 + pos, PACK == 2 ? base_at_2bit(tile_a, src) : lds8(tile_a + (uint32_t)src));
             }
         }
         const int nb = t.y & RUN_COUNT_MASK;
-        if (nb > 0) {
+        if (nb > 0 && PACK == 2) {
+            // two-bit source: one (unaligned) 32-bit window per 16 output bases, expanded in registers
+            int bidx = t.z + 16 * lane;                                      // source base index of this lane's vector
+            uint8_t* d = base32 + t.x + 16 * lane;
+            const int sh = 2 * (t.z & 15);                                   // warp-uniform, loop-invariant
+#pragma unroll 1
+            for (int v = lane; v < nb; v += 32, bidx += 512, d += 512) {
+                const uint32_t wa = tile_a + (uint32_t)((bidx >> 4) << 2);
+                st128<POLICY>(d, expand16(__funnelshift_r(lds32(wa), lds32(wa + 4), sh)));
+            }
+        } else if (nb > 0) {
             const int mis = t.z & 15;
             const uint32_t qa = tile_a + (uint32_t)(t.z - mis) + 16u * lane;
             uint8_t* d = base32 + t.x + 16 * lane;
@@ -720,7 +752,7 @@ __device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32
 #define EMIT_FRONT_PAD 32
 #define EMIT_BACK_PAD  64
 
-template <int POLICY, int MIN_CTAS>
+template <int POLICY, int MIN_CTAS, int PACK>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 k_emit(const EmitParams p)
 {
@@ -740,11 +772,11 @@ k_emit(const EmitParams p)
 
     const uint32_t dsm_a = smem_u32(dsm);
     const uint32_t tile_a = dsm_a + EMIT_FRONT_PAD;
-    const uint32_t len_a = tile_a + (uint32_t)p.tile_bytes + EMIT_BACK_PAD;
+    const uint32_t len_a = tile_a + (uint32_t)p.tile_smem_bytes + EMIT_BACK_PAD;
     const uint32_t src_a = len_a + 4u * (uint32_t)p.slot_cap;
     const uint32_t rt_a = src_a + 4u * (uint32_t)p.slot_cap + (uint32_t)warp * (uint32_t)(p.rt_cap + 2) * 24u;   // table A (8 B) + table B (16 B) per entry
     const uint32_t rtb_a = rt_a + (uint32_t)(p.rt_cap + 2) * 8u;
-    int32_t* sm_len = reinterpret_cast<int32_t*>(dsm + EMIT_FRONT_PAD + p.tile_bytes + EMIT_BACK_PAD);
+    int32_t* sm_len = reinterpret_cast<int32_t*>(dsm + EMIT_FRONT_PAD + p.tile_smem_bytes + EMIT_BACK_PAD);
     int32_t* sm_src = sm_len + p.slot_cap;
     const bool slots_staged = nslots <= p.slot_cap;
 
@@ -753,8 +785,8 @@ k_emit(const EmitParams p)
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const uint32_t bytes = (uint32_t)p.tile_bytes;
-            const uint8_t* src = p.seq + (size_t)tile * p.tile_bytes;
+            const uint32_t bytes = (uint32_t)p.tile_smem_bytes;
+            const uint8_t* src = p.seq + (size_t)tile * p.tile_smem_bytes;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(tile_a), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
@@ -824,7 +856,7 @@ k_emit(const EmitParams p)
                 if (done || nr + 17 > p.rt_cap) {               // tile finished, or table full: emit what we have
                     if (nr > 0) {
                         if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                        emit_runs<POLICY>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
+                        emit_runs<POLICY, PACK>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
                         nr = 0; carry = 0u;
                     }
                     if (done) break;
@@ -1020,7 +1052,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     if (!c) return GM2_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* frees[] = {c->d_seq, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
+    void* frees[] = {c->d_seq, c->d_seq2, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
                      c->d_first_gene, c->d_next_same, c->d_forced_ids, c->d_force_keep, c->d_counts, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
                      c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
@@ -1052,7 +1084,8 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
         if (value < 0 || value > (1 << 20)) return fail(c, GM2_ERR_INVALID, "emit batch out of range");
         c->emit_batch = (int)value; return GM2_OK;
     case GM2_CFG_PACKING:
-        if (value != 0 && value != 1) return fail(c, GM2_ERR_INVALID, "packing: only 0 (auto) and 1 (byte) are implemented");
+        if (c->have_ref) return fail(c, GM2_ERR_STATE, "GM2_CFG_PACKING must be set before gm2_set_reference");
+        if (value < 0 || value > 2) return fail(c, GM2_ERR_INVALID, "packing must be 0 (auto: byte), 1 (byte) or 2 (two-bit, ACGT only)");
         c->packing_req = (int)value; return GM2_OK;
     case GM2_CFG_STORE_POLICY:
         if (value != 0 && value != 1) return fail(c, GM2_ERR_INVALID, "store policy must be 0 or 1");
@@ -1206,6 +1239,21 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
     c->G = G; c->F = F; c->FW = (F + 31) / 32;
     c->ntiles = ntiles; c->nseg = nseg; c->nslots = (int)slot_src.size(); c->SW = c->nslots / 32;
     c->packing = 1; c->max_tile_slots = max_tile_slots;
+    if (c->d_seq2) { cudaFree(c->d_seq2); c->d_seq2 = nullptr; }
+    if (c->packing_req == 2) {
+        // measured slower than bytes (profiles/r01_emit_experiments.md) — kept as a selectable form
+        std::vector<uint8_t> packed((size_t)ntiles * (size_t)(T / 4) + 256, 0);
+        for (int64_t i = 0; i < G; ++i) {
+            uint8_t code;
+            switch (seq[i]) {
+            case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
+            default: return fail(c, GM2_ERR_INVALID, "gm2_set_reference: two-bit packing needs an upper-case ACGT-only sequence");
+            }
+            packed[(size_t)(i >> 2)] |= (uint8_t)(code << (2 * (i & 3)));
+        }
+        if ((rc = dev_upload(c, &c->d_seq2, packed))) return rc;
+        c->packing = 2;
+    }
     c->have_ref = true; c->planned = false; c->host_plan = false; c->mode = 0; c->S = 0;
     return GM2_OK;
 }
@@ -1485,20 +1533,25 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     const int64_t blocks = nbatch * tiles;
     if (blocks > 0x7fffffffLL) return fail(c, GM2_ERR_INVALID, "gm2_emit: grid too large; emit a smaller sample range");
     EmitParams p;
-    p.seq = c->d_seq; p.tile_slot = c->d_tile_slot; p.slot_src = c->d_slot_src; p.slot_len = c->d_slot_len;
+    const bool two_bit = c->packing == 2;
+    p.seq = two_bit ? c->d_seq2 : c->d_seq; p.tile_smem_bytes = two_bit ? c->tile_bytes / 4 : c->tile_bytes;
+    p.tile_slot = c->d_tile_slot; p.slot_src = c->d_slot_src; p.slot_len = c->d_slot_len;
     p.segkept = c->d_segkept; p.tile_off = c->d_tile_off; p.lengths = c->d_len; p.rec_off = c->d_rec_off;
     p.out = dev_out; p.s0 = s0; p.s1 = s1; p.first_idx = c->first_idx;
     p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW; p.batch = (int)batch; p.nbatch = (int)nbatch;
     p.rt_cap = c->rt_cap;
     p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
     p.prefix = c->prefix; p.debug = c->debug; p.order = c->order;
-    const size_t sm = 32 + (size_t)c->tile_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 24;
+    const size_t sm = 32 + (size_t)p.tile_smem_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 24;
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
     // register budget follows the shared-memory footprint: small tiles -> 4+ CTAs/SM (64 regs),
     // large tiles -> 3 CTAs/SM (up to 85 regs)
     const bool dense = sm <= 56 * 1024;
-    void (*kern)(const EmitParams) =
-        c->store_policy == 1 ? (dense ? k_emit<1, 4> : k_emit<1, 3>) : (dense ? k_emit<0, 4> : k_emit<0, 3>);
+    void (*kern)(const EmitParams);
+    if (two_bit)
+        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 2> : k_emit<1, 3, 2>) : (dense ? k_emit<0, 4, 2> : k_emit<0, 3, 2>);
+    else
+        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 1> : k_emit<1, 3, 1>) : (dense ? k_emit<0, 4, 1> : k_emit<0, 3, 1>);
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     kern<<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
     LAUNCH_CHECK(c, "k_emit");

@@ -49,7 +49,7 @@ extern "C" {
 #define GM2_CFG_TILE_BYTES    1  /* reference bases staged per CTA (multiple of 4096; before set_reference) */
 #define GM2_CFG_EMIT_WARPS    2  /* warps per emit CTA (1..8)                                */
 #define GM2_CFG_EMIT_BATCH    3  /* samples per emit CTA; 0 = choose from S and the SM count */
-#define GM2_CFG_PACKING       4  /* 0 auto, 1 byte/base, 2 two-bit (ACGT-only references)    */
+#define GM2_CFG_PACKING       4  /* 0 auto (= byte, the measured-faster form), 1 byte/base, 2 two-bit (ACGT-only; before set_reference) */
 #define GM2_CFG_STORE_POLICY  5  /* 0 plain stores, 1 streaming st.global.cs (default)       */
 #define GM2_CFG_RUN_TABLE     6  /* kept-run table entries per warp in shared memory (32..1024) */
 #define GM2_CFG_ORDER         8  /* emit CTA order: 0 tile-major, 1 sample-major (default)   */

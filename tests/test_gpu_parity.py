@@ -460,3 +460,32 @@ def test_huge_record_ids_render_all_digits():
             ctx.load_keep_host(rows)
             ctx.plan(first)
             assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+def test_two_bit_packing_is_byte_identical_and_rejects_iupac():
+    """GM2_CFG_PACKING=2 (2 bits per base in shared memory) must give the same image; a reference
+    with any non-ACGT letter is refused for that packing."""
+    rng = np.random.default_rng(5)
+    for G, F, seed, kw in [(200_000, 180, 81, dict(nested=5)), (65_537, 900, 82, dict(overlap_frac=0.5, nested=20)),
+                           (49_152 * 2, 40, 83, {}), (33, 2, 84, dict(nested=0))]:
+        g = synth.make_genome(G, F, seed, **kw)
+        starts, ends = g.starts_ends()
+        S = 29
+        rows = synth.pack_keep_rows(synth.random_keep_bool(len(g.genes), S, np.linspace(0.05, 0.95, S), seed=seed))
+        exp_len, _, exp_img = _oracle_image(g.seq, starts, ends, rows)
+        for policy in (0, 1):
+            with _native.Context(0) as ctx:
+                ctx.configure(_native.CFG_PACKING, 2)
+                ctx.configure(_native.CFG_STORE_POLICY, policy)
+                ctx.set_reference(g.seq, starts, ends)
+                assert ctx.query(_native.Q_PACKING) == 2
+                ctx.load_keep_host(rows)
+                ctx.plan(0)
+                assert np.array_equal(ctx.lengths(), exp_len)
+                assert np.array_equal(_gpu_image(ctx, S), exp_img)
+    g = synth.make_genome(5_000, 10, 85, iupac_runs=3)
+    with _native.Context(0) as ctx:
+        ctx.configure(_native.CFG_PACKING, 2)
+        with pytest.raises(_native.Gm2Error) as ei:
+            ctx.set_reference(g.seq, *g.starts_ends())
+        assert ei.value.code == _native.ERR_INVALID and "ACGT" in str(ei.value)
