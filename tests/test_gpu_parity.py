@@ -489,3 +489,48 @@ def test_two_bit_packing_is_byte_identical_and_rejects_iupac():
         with pytest.raises(_native.Gm2Error) as ei:
             ctx.set_reference(g.seq, *g.starts_ends())
         assert ei.value.code == _native.ERR_INVALID and "ACGT" in str(ei.value)
+
+
+def test_fuzz_kernel_configurations():
+    """Random genomes x random kernel configurations (tile size, warps, run-table size, packing,
+    store policy, CTA order, batch) against the C oracle, byte for byte."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(48):
+        G = int(rng.choice([1, 31, 32, 33, 4095, 4096, 4097, int(rng.integers(5_000, 140_000))]))
+        F = int(rng.integers(0, 400)) if G > 100 else int(rng.integers(0, 4))
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G)]
+        style = trial % 4
+        if style == 0:      # gene-like
+            starts = np.sort(rng.integers(0, max(G - 1, 1), F)).astype(np.int64)
+            ends = starts + rng.integers(1, max(G // max(F, 1) * 2, 2), F)
+        elif style == 1:    # tiny runs everywhere
+            starts = np.sort(rng.integers(0, max(G - 1, 1), F)).astype(np.int64)
+            ends = starts + rng.integers(0, 40, F)
+        elif style == 2:    # heavy overlap / nesting
+            starts = rng.integers(0, max(G // 2, 1), F).astype(np.int64)
+            ends = starts + rng.integers(0, max(G // 2, 2), F)
+        else:               # degenerate and out-of-range intervals mixed in
+            starts = rng.integers(-100, G + 100, F).astype(np.int64)
+            ends = starts + rng.integers(-50, max(G // 10, 5), F)
+        S = int(rng.integers(1, 40))
+        p = rng.random((S, 1)) if trial % 3 else np.full((S, 1), rng.choice([0.02, 0.98]))
+        rows = synth.pack_keep_rows(rng.random((S, F)) < p) if F else np.zeros((S, 0), dtype=np.uint32)
+        first = int(rng.choice([0, 9, 99, 12345, 99_999_990]))
+        exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows, first_idx=first)
+        cfg = {
+            _native.CFG_TILE_BYTES: int(rng.choice([4096, 8192, 16384, 32768, 49152, 65536, 131072])),
+            _native.CFG_EMIT_WARPS: int(rng.choice([1, 2, 4, 8])),
+            _native.CFG_RUN_TABLE: int(rng.choice([32, 34, 64, 128])),
+            _native.CFG_PACKING: int(rng.choice([1, 2])),
+            _native.CFG_STORE_POLICY: int(rng.choice([0, 1])),
+            _native.CFG_ORDER: int(rng.choice([0, 1])),
+            _native.CFG_EMIT_BATCH: int(rng.choice([0, 1, 3, 16])),
+        }
+        with _native.Context(0) as ctx:
+            for k, v in cfg.items():
+                ctx.configure(k, v)
+            ctx.set_reference(seq, starts, ends)
+            ctx.load_keep_host(rows.reshape(S, -1) if F else np.zeros((S, 0), dtype=np.uint32))
+            ctx.plan(first)
+            assert np.array_equal(ctx.lengths(), exp_len), (trial, cfg)
+            assert np.array_equal(_gpu_image(ctx, S), exp_img), (trial, G, F, S, cfg)

@@ -6,7 +6,7 @@ chunks (it never exists at once), and sampled records are verified against the C
 device-side record hash.  Keep rows are generated on the device (torch) — 1M x 10k Python strings
 is not a workload.  Prints one JSON line."""
 import argparse, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from genome_minimizer_2_b200 import _native, synth
