@@ -79,6 +79,7 @@ struct gm2_ctx {
     int32_t V = 0;
     int32_t *d_first_gene = nullptr, *d_next_same = nullptr;
     uint32_t *d_forced_ids = nullptr, *d_force_keep = nullptr;     // optional (gm2_set_forced)
+    uint32_t *d_has_gene = nullptr;                                // one bit per name id: names at least one gene
     const float* probs = nullptr; int64_t probs_ld = 0; float probs_thr = 0.5f;   // mode 3 (borrowed)
     int64_t* d_counts = nullptr; int64_t counts_cap = 0;
 
@@ -251,37 +252,52 @@ k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off
 __global__ void __launch_bounds__(256)
 k_keep_from_probs(const float* __restrict__ probs, int64_t S, int64_t V, int64_t ld, float thr,
                   const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
-                  const uint32_t* __restrict__ forced_ids, const uint32_t* __restrict__ force_keep,
-                  int FW, uint32_t* __restrict__ keep, int64_t* __restrict__ counts)
+                  const uint32_t* __restrict__ has_gene, const uint32_t* __restrict__ forced_ids,
+                  const uint32_t* __restrict__ force_keep, int FW, int VW, uint32_t* __restrict__ keep,
+                  int64_t* __restrict__ counts)
 {
-    extern __shared__ uint32_t kp_row[];
+    // shared: keep row (FW words) | has-gene bitmap (VW+1 words) | forced-id bitmap (VW+1 words, zeros if none)
+    extern __shared__ uint32_t kp_sm[];
+    uint32_t* kp_row = kp_sm;
+    uint32_t* hg = kp_sm + FW;
+    uint32_t* fo = hg + VW + 1;
     __shared__ int s_count;
     const int64_t s = blockIdx.x;
     for (int i = threadIdx.x; i < FW; i += blockDim.x) kp_row[i] = force_keep ? force_keep[i] : 0u;
+    for (int i = threadIdx.x; i <= VW; i += blockDim.x) {
+        hg[i] = i < VW ? has_gene[i] : 0u;
+        fo[i] = (forced_ids && i < VW) ? forced_ids[i] : 0u;
+    }
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     const float* p = probs + s * ld;
     int cnt = 0;
-    auto visit = [&](int64_t c, float v) {
-        if (v > thr) {
-            ++cnt;
-            for (int g = __ldg(first_gene + c); g >= 0; g = __ldg(next_same + g)) atomicOr(&kp_row[g >> 5], 1u << (g & 31));
-        } else if (forced_ids && ((__ldg(forced_ids + (c >> 5)) >> (c & 31)) & 1u)) {
-            ++cnt;                                   // an essential the reference appends to the list
-        }
+    auto mark = [&](int64_t c) {
+        for (int g = __ldg(first_gene + c); g >= 0; g = __ldg(next_same + g)) atomicOr(&kp_row[g >> 5], 1u << (g & 31));
+    };
+    auto visit1 = [&](int64_t c, float v) {
+        const uint32_t bit = 1u << (c & 31);
+        if (v > thr) { ++cnt; if (hg[c >> 5] & bit) mark(c); }
+        else if (fo[c >> 5] & bit) ++cnt;            // an essential the reference appends to the list
     };
     int64_t head = (int64_t)(((16u - (uint32_t)((uintptr_t)p & 15u)) & 15u) >> 2);
     if (head > V) head = V;
-    if (threadIdx.x < head) visit(threadIdx.x, __ldg(p + threadIdx.x));
+    if (threadIdx.x < head) visit1(threadIdx.x, __ldg(p + threadIdx.x));
     const float4* v4 = reinterpret_cast<const float4*>(p + head);
     const int64_t nvec = (V - head) >> 2;
     for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
         const float4 v = __ldg(v4 + i);
         const int64_t c = head + 4 * i;
-        visit(c, v.x); visit(c + 1, v.y); visit(c + 2, v.z); visit(c + 3, v.w);
+        const uint32_t m = (v.x > thr ? 1u : 0u) | (v.y > thr ? 2u : 0u) | (v.z > thr ? 4u : 0u) | (v.w > thr ? 8u : 0u);
+        const int w = (int)(c >> 5), sh = (int)(c & 31);
+        const uint32_t hg4 = __funnelshift_r(hg[w], hg[w + 1], sh) & 0xfu;      // 4 bitmap bits, may straddle words
+        const uint32_t fo4 = __funnelshift_r(fo[w], fo[w + 1], sh) & 0xfu;
+        cnt += __popc(m) + __popc(~m & fo4);
+        uint32_t todo = m & hg4;                                               // present columns that name a gene: rare
+        while (todo) { const int j = __ffs(todo) - 1; todo &= todo - 1; mark(c + j); }
     }
     const int64_t tail0 = head + 4 * nvec;
-    if (tail0 + threadIdx.x < V) visit(tail0 + threadIdx.x, __ldg(p + tail0 + threadIdx.x));
+    if (tail0 + threadIdx.x < V) visit1(tail0 + threadIdx.x, __ldg(p + tail0 + threadIdx.x));
     cnt = __reduce_add_sync(FULL_MASK, cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
     __syncthreads();
@@ -1053,7 +1069,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void* frees[] = {c->d_seq, c->d_seq2, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
-                     c->d_first_gene, c->d_next_same, c->d_forced_ids, c->d_force_keep, c->d_counts, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
+                     c->d_first_gene, c->d_next_same, c->d_forced_ids, c->d_force_keep, c->d_has_gene, c->d_counts, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
                      c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
     for (void* p : frees) if (p) cudaFree(p);
@@ -1284,6 +1300,11 @@ GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx,
     int rc;
     if ((rc = dev_upload(c, &c->d_first_gene, first))) return rc;
     if ((rc = dev_upload(c, &c->d_next_same, next))) return rc;
+    {
+        std::vector<uint32_t> hg(((size_t)V + 31) / 32 + 1, 0u);
+        for (int32_t id = 0; id < V; ++id) if (first[id] >= 0) hg[(size_t)id >> 5] |= 1u << (id & 31);
+        if ((rc = dev_upload(c, &c->d_has_gene, hg))) return rc;
+    }
     c->V = V;
     if (c->d_forced_ids) { cudaFree(c->d_forced_ids); c->d_forced_ids = nullptr; }
     if (c->d_force_keep) { cudaFree(c->d_force_keep); c->d_force_keep = nullptr; }
@@ -1407,11 +1428,13 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         if ((rc = dev_reserve(c, &c->d_counts, &c->counts_cap, S))) return rc;
         keep = c->own_keep;
         if (S > 0) {
-            const size_t sm = (size_t)std::max(c->FW, 1) * 4;
+            const int VW = (c->V + 31) / 32;
+            const size_t sm = ((size_t)c->FW + 2 * ((size_t)VW + 1)) * 4;
+            if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: too many name ids for the dense keep builder's bitmaps");
             if (sm > 48 * 1024) CU(c, cudaFuncSetAttribute(k_keep_from_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_keep_from_probs<<<(unsigned)S, 256, sm, c->stream>>>(c->probs, S, c->V, c->probs_ld, c->probs_thr, c->d_first_gene,
-                                                                c->d_next_same, c->d_forced_ids, c->d_force_keep, c->FW,
-                                                                c->own_keep, c->d_counts);
+                                                                c->d_next_same, c->d_has_gene, c->d_forced_ids, c->d_force_keep,
+                                                                c->FW, VW, c->own_keep, c->d_counts);
             LAUNCH_CHECK(c, "k_keep_from_probs");
         }
     }
