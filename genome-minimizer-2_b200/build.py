@@ -32,7 +32,9 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(p) > t for p in (SRC, HDR))
+    csrc = os.path.dirname(SRC)
+    deps = [HDR] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    return any(os.path.getmtime(p) > t for p in deps)
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:

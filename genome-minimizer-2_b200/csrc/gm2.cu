@@ -31,16 +31,20 @@
 #define GM2_API extern "C" __attribute__((visibility("default")))
 
 // ------------------------------------------------------------------------------------------
+// kernels (one translation unit; each header documents the reference lines it replaces)
+// ------------------------------------------------------------------------------------------
+#include "device_util.cuh"
+#include "k1_keep.cuh"
+#include "k2_plan.cuh"
+#include "k3_scan.cuh"
+#include "k4_emit.cuh"
+#include "diag.cuh"
+
+// ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
 
 static const char kDefaultPrefix[] = "Minimized_E_coli_K12_MG1655_";   // minimizer_2.py:476
-#define GM2_MAX_PREFIX 95
-
-struct HeaderPrefix {            // passed by value to kernels; text[0] is '>'
-    int  len;
-    char text[GM2_MAX_PREFIX + 1];
-};
 
 struct gm2_ctx {
     int device = 0;
@@ -54,7 +58,7 @@ struct gm2_ctx {
     uint64_t launches = 0;
 
     // configuration
-    int tile_bytes = 49152;        // 4 CTAs/SM of 8 warps with the 64-register kernel variant: best measured (profiles/)
+    int tile_bytes = 49152;        // best measured (profiles/r01_emit_experiments.md): 3 CTAs of 8 warps per SM
     int emit_warps = 8;
     int emit_batch = 0;
     int packing_req = 0;
@@ -140,867 +144,6 @@ static int dev_upload(gm2_ctx* c, T** p, const std::vector<T>& v) {
     if (!v.empty()) CU(c, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return GM2_OK;
 }
-
-// ------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------
-
-#define FULL_MASK 0xffffffffu
-
-__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(FULL_MASK, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
-    return v;
-}
-__device__ __forceinline__ long long warp_incl_scan64(long long v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        long long t = __shfl_up_sync(FULL_MASK, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
-__constant__ unsigned long long c_pow10[20] = {
-    1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
-    1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
-    100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull,
-    1000000000000000000ull, 10000000000000000000ull};
-
-__device__ __forceinline__ int ndigits_u64(unsigned long long v) {
-    int n = 1;
-    while (n < 20 && v >= c_pow10[n]) ++n;
-    return n;
-}
-
-// ------------------------------------------------------------------------------------------
-// K1  keep-mask builder: name-id lists -> F-bit keep rows          (minimizer_2.py:59-63)
-//   One warp per sample, CTAs loop over groups of samples.  The static name table is a
-//   linked list through the genes (first_gene[id] -> next_same_name[g] -> ...), staged in
-//   shared memory when it fits, so an id costs one coalesced global load plus shared-memory
-//   lookups; the row is assembled in shared memory with atomicOr and written out coalesced.
-// ------------------------------------------------------------------------------------------
-#define K1_WARPS 8
-__global__ void __launch_bounds__(K1_WARPS * 32, 4)
-k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V, int32_t F,
-                const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
-                int FW, uint32_t* __restrict__ keep, int map_in_smem)
-{
-    extern __shared__ uint32_t k1_sm[];
-    uint32_t* rows = k1_sm;                                          // K1_WARPS x FW
-    const int32_t* fg = first_gene;
-    const int32_t* nx = next_same;
-    if (map_in_smem) {
-        int32_t* s_fg = reinterpret_cast<int32_t*>(k1_sm + (size_t)K1_WARPS * FW);
-        int32_t* s_nx = s_fg + V;
-        for (int i = threadIdx.x; i < V; i += blockDim.x) s_fg[i] = first_gene[i];
-        for (int i = threadIdx.x; i < F; i += blockDim.x) s_nx[i] = next_same[i];
-        fg = s_fg; nx = s_nx;
-        __syncthreads();
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* row = rows + (size_t)warp * FW;
-    for (int64_t s = (int64_t)blockIdx.x * K1_WARPS + warp; s < S; s += (int64_t)gridDim.x * K1_WARPS) {
-        for (int i = lane; i < FW; i += 32) row[i] = 0u;
-        __syncwarp();
-        const int64_t b = off[s], e = off[s + 1];
-        auto mark = [&](int32_t id) {
-            if ((uint32_t)id < (uint32_t)V)
-                for (int g = fg[id]; g >= 0; g = nx[g]) atomicOr(&row[g >> 5], 1u << (g & 31));
-        };
-        // head up to a 16-byte boundary, 128-bit body (two vectors per lane in flight), scalar tail
-        const int64_t b4 = min((b + 3) & ~(int64_t)3, e), e4 = b4 + ((e - b4) & ~(int64_t)3);
-        if (b + lane < b4) mark(__ldg(ids + b + lane));
-        const int4* v4 = reinterpret_cast<const int4*>(ids + b4);
-        const int64_t nv = (e4 - b4) >> 2;
-        for (int64_t i0 = 0; i0 < nv; i0 += 128) {
-            int4 x[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + 32 * u + lane;
-                x[u] = i < nv ? __ldg(v4 + i) : make_int4(-1, -1, -1, -1);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { mark(x[u].x); mark(x[u].y); mark(x[u].z); mark(x[u].w); }
-        }
-        if (e4 + lane < e) mark(__ldg(ids + e4 + lane));
-        __syncwarp();
-        uint32_t* dst = keep + (size_t)s * FW;
-        for (int i = lane; i < FW; i += 32) dst[i] = row[i];
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K1'  keep-mask builder from dense probabilities (BASELINE config 5):
-//   the reference's  decode -> `> 0.5` (utils/extras.py:200-201) -> masks_to_gene_lists `>= 0.5`
-//   on the 0/1 matrix (explore_data/binary_converter.py:55,:64) -> check_essential_genes adds the
-//   missing essentials (:91-98) -> `name in needed` (minimizer_2.py:62), collapsed: column c is a
-//   name id; it is "present" iff probs[s][c] > threshold; a gene is kept iff its name's column is
-//   present or it is forced (essential).  counts[s] = length of the list the reference would
-//   have built = present columns + forced ids that are not present (+ a host-side constant for
-//   essentials that are no column at all).  One CTA per sample, coalesced 128-bit reads.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_keep_from_probs(const float* __restrict__ probs, int64_t S, int64_t V, int64_t ld, float thr,
-                  const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
-                  const uint32_t* __restrict__ has_gene, const uint32_t* __restrict__ forced_ids,
-                  const uint32_t* __restrict__ force_keep, int FW, int VW, uint32_t* __restrict__ keep,
-                  int64_t* __restrict__ counts)
-{
-    // shared: keep row (FW words) | has-gene bitmap (VW+1 words) | forced-id bitmap (VW+1 words, zeros if none)
-    extern __shared__ uint32_t kp_sm[];
-    uint32_t* kp_row = kp_sm;
-    uint32_t* hg = kp_sm + FW;
-    uint32_t* fo = hg + VW + 1;
-    __shared__ int s_count;
-    const int64_t s = blockIdx.x;
-    for (int i = threadIdx.x; i < FW; i += blockDim.x) kp_row[i] = force_keep ? force_keep[i] : 0u;
-    for (int i = threadIdx.x; i <= VW; i += blockDim.x) {
-        hg[i] = i < VW ? has_gene[i] : 0u;
-        fo[i] = (forced_ids && i < VW) ? forced_ids[i] : 0u;
-    }
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    const float* p = probs + s * ld;
-    int cnt = 0;
-    auto mark = [&](int64_t c) {
-        for (int g = __ldg(first_gene + c); g >= 0; g = __ldg(next_same + g)) atomicOr(&kp_row[g >> 5], 1u << (g & 31));
-    };
-    auto visit1 = [&](int64_t c, float v) {
-        const uint32_t bit = 1u << (c & 31);
-        if (v > thr) { ++cnt; if (hg[c >> 5] & bit) mark(c); }
-        else if (fo[c >> 5] & bit) ++cnt;            // an essential the reference appends to the list
-    };
-    int64_t head = (int64_t)(((16u - (uint32_t)((uintptr_t)p & 15u)) & 15u) >> 2);
-    if (head > V) head = V;
-    if (threadIdx.x < head) visit1(threadIdx.x, __ldg(p + threadIdx.x));
-    const float4* v4 = reinterpret_cast<const float4*>(p + head);
-    const int64_t nvec = (V - head) >> 2;
-    for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const float4 v = __ldg(v4 + i);
-        const int64_t c = head + 4 * i;
-        const uint32_t m = (v.x > thr ? 1u : 0u) | (v.y > thr ? 2u : 0u) | (v.z > thr ? 4u : 0u) | (v.w > thr ? 8u : 0u);
-        const int w = (int)(c >> 5), sh = (int)(c & 31);
-        const uint32_t hg4 = __funnelshift_r(hg[w], hg[w + 1], sh) & 0xfu;      // 4 bitmap bits, may straddle words
-        const uint32_t fo4 = __funnelshift_r(fo[w], fo[w + 1], sh) & 0xfu;
-        cnt += __popc(m) + __popc(~m & fo4);
-        uint32_t todo = m & hg4;                                               // present columns that name a gene: rare
-        while (todo) { const int j = __ffs(todo) - 1; todo &= todo - 1; mark(c + j); }
-    }
-    const int64_t tail0 = head + 4 * nvec;
-    if (tail0 + threadIdx.x < V) visit1(tail0 + threadIdx.x, __ldg(p + tail0 + threadIdx.x));
-    cnt = __reduce_add_sync(FULL_MASK, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
-    __syncthreads();
-    uint32_t* dst = keep + (size_t)s * FW;
-    for (int i = threadIdx.x; i < FW; i += blockDim.x) dst[i] = kp_row[i];
-    if (threadIdx.x == 0) counts[s] = s_count;
-}
-
-// ------------------------------------------------------------------------------------------
-// K2 + K3a  plan: per sample, segment kept-flags and the exclusive scan of kept lengths
-//   (minimizer_2.py:75-80 union-of-ranges, :94-96 running output index)
-//   One CTA per PLAN_NS samples (the static tables are read once for all of them).  Segment
-//   slots are laid out per genome tile, each tile's slots padded to a multiple of 32 so that
-//   one ballot == one stored word and k_emit reads whole words.  Per slot the covering genes
-//   are inlined as a pair (x, y): -1 = none; y <= -2 points into an overflow list for the rare
-//   slot covered by more than two genes.  A warp takes one tile at a time: branch-free bit tests,
-//   one ballot per 32 slots and sample, kept lengths accumulated in registers and reduced once per
-//   tile (REDUX); warp k then scans the tile sums of sample k.
-// ------------------------------------------------------------------------------------------
-#define PLAN_NS 4
-__device__ __forceinline__ bool keep_bit(const uint32_t* row, int g) {
-    return g < 0 ? true : ((row[g >> 5] >> (g & 31)) & 1u) != 0u;
-}
-
-__global__ void __launch_bounds__(256)
-k_plan(int64_t S, int FW, const uint32_t* __restrict__ keep, int ntiles,
-       const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_len,
-       const int2* __restrict__ slot_cov, const int32_t* __restrict__ cov_ovf,
-       int SW, uint32_t* __restrict__ segkept, int32_t* __restrict__ tile_off,
-       int64_t* __restrict__ lengths, int64_t* __restrict__ rec_size,
-       int64_t first_idx, int prefix_len)
-{
-    extern __shared__ uint32_t plan_sm[];
-    uint32_t* rows = plan_sm;                                   // PLAN_NS x FW
-    int32_t* tl = (int32_t*)(plan_sm + (size_t)PLAN_NS * FW);   // PLAN_NS x ntiles kept lengths
-    const int64_t sbase = (int64_t)blockIdx.x * PLAN_NS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-
-    for (int i = threadIdx.x; i < PLAN_NS * FW; i += blockDim.x) {
-        const int64_t s = sbase + i / FW;
-        rows[i] = s < S ? keep[(size_t)s * FW + (i % FW)] : 0u;
-    }
-    __syncthreads();
-
-    uint32_t* skw = (uint32_t*)(tl + PLAN_NS * ntiles);           // PLAN_NS x SW kept-bit words, staged
-
-    for (int t = warp; t < ntiles; t += nwarps) {
-        const int c0 = __ldg(tile_slot + t) >> 5, c1 = __ldg(tile_slot + t + 1) >> 5;   // 32-slot chunks of the tile
-        int acc[PLAN_NS];
-#pragma unroll
-        for (int k = 0; k < PLAN_NS; ++k) acc[k] = 0;
-        for (int c = c0; c < c1; ++c) {
-            const int slot = 32 * c + lane;
-            const int len = __ldg(slot_len + slot);
-            const int2 cv = __ldg(slot_cov + slot);
-            // branch-free bit tests: word/shift of both covering genes, computed once for all samples
-            const int gx = cv.x < 0 ? 0 : cv.x, gy = cv.y < 0 ? 0 : cv.y;
-            const int wx = gx >> 5, wy = gy >> 5;
-            const uint32_t sx = gx & 31, sy = gy & 31;
-            const uint32_t fx = cv.x < 0 ? 1u : 0u, fy = cv.y < 0 ? 1u : 0u;     // "no gene" counts as kept
-            const uint32_t live = len > 0 ? 1u : 0u;                            // padding slots have len 0
-            uint32_t kb[PLAN_NS];
-#pragma unroll
-            for (int k = 0; k < PLAN_NS; ++k) {
-                const uint32_t* row = rows + k * FW;
-                kb[k] = live & ((row[wx] >> sx) | fx) & ((row[wy] >> sy) | fy) & 1u;
-            }
-            if (__any_sync(FULL_MASK, cv.y < -1)) {                             // rare: > 2 covering genes
-                if (cv.y < -1) {
-                    const int32_t* o = cov_ovf + (-cv.y - 2);
-                    const int n = __ldg(o);
-                    for (int j = 1; j <= n; ++j) {
-                        const int g = __ldg(o + j);
-#pragma unroll
-                        for (int k = 0; k < PLAN_NS; ++k) kb[k] &= (rows[k * FW + (g >> 5)] >> (g & 31)) & 1u;
-                    }
-                }
-                __syncwarp();
-            }
-#pragma unroll
-            for (int k = 0; k < PLAN_NS; ++k) {
-                const uint32_t w = __ballot_sync(FULL_MASK, kb[k] != 0u);
-                if (lane == 0) skw[k * SW + c] = w;
-                acc[k] += kb[k] ? len : 0;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < PLAN_NS; ++k) {
-            const int v = __reduce_add_sync(FULL_MASK, acc[k]);
-            if (lane == 0) tl[k * ntiles + t] = v;
-        }
-    }
-    __syncthreads();
-    // kept-bit rows out, coalesced
-    for (int i = threadIdx.x; i < PLAN_NS * SW; i += blockDim.x) {
-        const int64_t s = sbase + i / SW;
-        if (s < S) segkept[(size_t)s * SW + (i % SW)] = skw[i];
-    }
-    __syncthreads();
-    if (warp < PLAN_NS && sbase + warp < S) {
-        const int64_t s = sbase + warp;
-        const int32_t* mytl = tl + warp * ntiles;
-        int carry = 0;
-        int32_t* to = tile_off + (size_t)s * ntiles;
-        for (int base = 0; base < ntiles; base += 32) {
-            const int t = base + lane;
-            const int v = t < ntiles ? mytl[t] : 0;
-            const int incl = warp_incl_scan(v, lane);
-            if (t < ntiles) to[t] = carry + incl - v;
-            carry += __shfl_sync(FULL_MASK, incl, 31);
-        }
-        if (lane == 0) {
-            lengths[s] = carry;
-            const int nd = ndigits_u64((unsigned long long)(first_idx + s + 1));
-            rec_size[s] = (int64_t)prefix_len + nd + 1 + carry + 1;   // '>'+prefix, digits, '\n', bases, '\n'
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K3b  across-sample exclusive scan of record sizes (int64): single pass, chained scan
-//   with decoupled look-back.  One 64-bit descriptor per tile = {2-bit status, 62-bit value},
-//   tile ids handed out by an atomic ticket so every predecessor is already running.
-// ------------------------------------------------------------------------------------------
-#define SCAN_THREADS 256
-#define SCAN_ITEMS   8
-#define SCAN_TILE    (SCAN_THREADS * SCAN_ITEMS)
-#define ST_INVALID   0ull
-#define ST_AGG       1ull
-#define ST_PREFIX    2ull
-#define ST_SHIFT     62
-#define ST_VALMASK   ((1ull << ST_SHIFT) - 1ull)
-
-__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_records(const int64_t* __restrict__ in, int64_t* __restrict__ out /* n+1 */, int64_t n,
-               unsigned long long* desc, unsigned int* ticket)
-{
-    __shared__ unsigned int s_tile;
-    __shared__ long long s_warp[SCAN_THREADS / 32];
-    __shared__ long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned int tile = s_tile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-
-    long long v[SCAN_ITEMS];
-    long long tsum = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const int64_t k = base + i;
-        v[i] = k < n ? in[k] : 0;
-        tsum += v[i];
-    }
-    const long long wincl = warp_incl_scan64(tsum, lane);
-    if (lane == 31) s_warp[warp] = wincl;
-    __syncthreads();
-    long long woff = 0, agg = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        const long long x = s_warp[w];
-        if (w < warp) woff += x;
-        agg += x;
-    }
-    // look-back by warp 0
-    if (warp == 0) {
-        long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_desc(desc, (ST_PREFIX << ST_SHIFT) | ((unsigned long long)agg & ST_VALMASK));
-        } else {
-            if (lane == 0) st_desc(desc + tile, (ST_AGG << ST_SHIFT) | ((unsigned long long)agg & ST_VALMASK));
-            long long look = (long long)tile - 1;
-            while (true) {
-                const long long idx = look - lane;
-                unsigned long long d = (ST_PREFIX << ST_SHIFT);          // virtual tile -1: prefix 0
-                if (idx >= 0) {
-                    do { d = ld_desc(desc + idx); } while ((d >> ST_SHIFT) == ST_INVALID);
-                }
-                const unsigned int is_prefix = __ballot_sync(FULL_MASK, (d >> ST_SHIFT) == ST_PREFIX);
-                // lanes 0..first-prefix-lane contribute (lane 0 = nearest predecessor)
-                const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 31;
-                long long val = lane <= stop ? (long long)(d & ST_VALMASK) : 0;
-#pragma unroll
-                for (int dd = 16; dd > 0; dd >>= 1) val += __shfl_xor_sync(FULL_MASK, val, dd);
-                excl += val;
-                if (is_prefix) break;
-                look -= 32;
-            }
-            if (lane == 0) st_desc(desc + tile, (ST_PREFIX << ST_SHIFT) | ((unsigned long long)(excl + agg) & ST_VALMASK));
-        }
-        if (lane == 0) s_prefix = excl;
-    }
-    __syncthreads();
-    long long run = s_prefix + woff + (wincl - tsum);
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        const int64_t k = base + i;
-        if (k < n) out[k] = run;
-        run += v[i];
-        if (k == n - 1) out[n] = run;
-    }
-    if (n == 0 && tile == 0 && threadIdx.x == 0) out[0] = 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// K4  emit: stream-compaction gather + FASTA framing              (minimizer_2.py:94-97, :476-477)
-//   CTA = (genome tile, batch of samples).  The tile's bases are staged ONCE in shared
-//   memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and reused by every sample
-//   of the batch.  Each warp owns one sample at a time: it reads the tile's kept-bit
-//   words, scans kept segment lengths with shuffles, and copies every maximal kept run
-//   shared->global with destination-aligned 128-bit stores (the source is re-phased with
-//   funnel shifts); only a run's <16-byte head and tail use byte stores.  The warp that
-//   owns tile 0 writes the '>' header, the one that owns the last tile the final '\n'.
-// ------------------------------------------------------------------------------------------
-struct EmitParams {
-    const uint8_t* seq;
-    const int32_t* tile_slot;
-    const int32_t* slot_src;
-    const int32_t* slot_len;
-    const uint32_t* segkept;
-    const int32_t* tile_off;
-    const int64_t* lengths;
-    const int64_t* rec_off;
-    uint8_t* out;
-    int64_t s0, s1;
-    int64_t first_idx;
-    int tile_bytes, ntiles, SW, batch, nbatch;
-    int tile_smem_bytes;   // bytes of the staged tile: tile_bytes (1 byte/base) or tile_bytes/4 (2 bits/base)
-    int rt_cap;            // run-table entries per warp (shared memory)
-    int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
-    int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
-    int debug;             // timing experiments only (wrong output; needs -DGM2_EMIT_DEBUG): 1 no boundary
-                           // sectors, 2 no interior stores, 4 interior stores without shared loads
-    HeaderPrefix prefix;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-// shared-memory accessors on 32-bit shared-window addresses.  Tile / slot-table reads are plain
-// (read-only after the CTA barrier, free to be scheduled); run-table accesses are volatile with a
-// memory clobber because the table is rewritten per (sample, tile) around __syncwarp().
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-    uint4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ int2 rt_load(uint32_t a) {
-    int2 v;
-    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void rt_store(uint32_t a, int x, int y) {
-    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void rt_store_x(uint32_t a, int x) {
-    asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(x) : "memory");
-}
-
-// POLICY 1 = streaming (evict-first) stores: the image is written once and never re-read here.
-template <int POLICY>
-__device__ __forceinline__ void st128(uint8_t* p, const uint4& v) {
-    if (POLICY == 1) __stcs(reinterpret_cast<uint4*>(p), v);
-    else *reinterpret_cast<uint4*>(p) = v;
-}
-template <int POLICY>
-__device__ __forceinline__ void st8(uint8_t* p, uint32_t v) {
-    if (POLICY == 1) __stcs(p, (uint8_t)v);
-    else *p = (uint8_t)v;
-}
-
-// One whole 32-byte sector from one lane (STG.256).
-__device__ __forceinline__ void st256(uint8_t* p, const uint4& a, const uint4& b) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-}
-
-// ---- 2-bit packing (ACGT-only references): base i of the tile sits in bits [2i, 2i+2) of the
-// little-endian bit stream, code 0..3 = A, C, G, T.  Sixteen bases = one 32-bit word.
-#define ACGT_LUT 0x54474341u                     // 'A' 'C' 'G' 'T' as bytes 0..3
-__device__ __forceinline__ uint32_t spread8(uint32_t t) {      // 8 two-bit codes -> 8 nibbles
-    t &= 0xffffu;
-    t = (t | (t << 8)) & 0x00ff00ffu;
-    t = (t | (t << 4)) & 0x0f0f0f0fu;
-    t = (t | (t << 2)) & 0x33333333u;
-    return t;
-}
-__device__ __forceinline__ uint4 expand16(uint32_t x) {       // 16 codes -> 16 ASCII bytes (PRMT as a 4-entry LUT)
-    const uint32_t lo = spread8(x), hi = spread8(x >> 16);
-    return make_uint4(__byte_perm(ACGT_LUT, 0u, lo), __byte_perm(ACGT_LUT, 0u, lo >> 16),
-                      __byte_perm(ACGT_LUT, 0u, hi), __byte_perm(ACGT_LUT, 0u, hi >> 16));
-}
-__device__ __forceinline__ uint32_t base_at_2bit(uint32_t tile_a, int b) {
-    const uint32_t w = lds32(tile_a + (uint32_t)((b >> 4) << 2));
-    return (ACGT_LUT >> (8u * ((w >> (2 * (b & 15))) & 3u))) & 0xffu;
-}
-
-// Interior of one kept run: nb destination-aligned 16-byte vectors, lanes strided by 32.
-// qa = this lane's 16-byte aligned shared address at or below its first source byte,
-// K = word phase (0..3), sh = byte phase in bits.
-template <int POLICY, int K>
-__device__ __forceinline__ void copy_vectors(uint32_t qa, uint8_t* __restrict__ d, int nb, int sh, int lane)
-{
-#pragma unroll 1
-    for (int v = lane; v < nb; v += 32, qa += 512, d += 512) {
-        const uint4 lo = lds128(qa);
-        const uint4 hi = lds128(qa + 16);
-        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        uint4 o;
-        o.x = __funnelshift_r(w[K], w[K + 1], sh);
-        o.y = __funnelshift_r(w[K + 1], w[K + 2], sh);
-        o.z = __funnelshift_r(w[K + 2], w[K + 3], sh);
-        o.w = __funnelshift_r(w[K + 3], w[K + 4], sh);
-        st128<POLICY>(d, o);
-    }
-}
-
-// 16 bytes from an arbitrarily aligned shared address (per-lane alignment).
-__device__ __forceinline__ uint4 fetch16(uint32_t a) {
-    const uint32_t a4 = a & ~3u;
-    const int sh = (int)(a & 3u) * 8;
-    const uint32_t w0 = lds32(a4), w1 = lds32(a4 + 4), w2 = lds32(a4 + 8), w3 = lds32(a4 + 12), w4 = lds32(a4 + 16);
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                      __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-__device__ __forceinline__ uint32_t low_bytes_mask(int n) {          // n bytes from the low end, n clamped to 0..4
-    return n >= 4 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
-}
-
-// One batch of kept runs of a (sample, tile): table A entry r = {Q_r, S_r}, entry nr = {end, -}.
-//   Q = destination offset in "Q space" (bytes from base32, a 32-byte aligned global pointer),
-//   S = source byte offset inside the shared-memory tile.  Output is contiguous: run r covers
-//   [Q_r, Q_{r+1}).
-// The warp writes ONE ASCENDING STREAM in units of 32-byte sectors, each sector exactly once and
-// in address order (measured with store-only models, profiles/r01_emit_experiments.md: a sector
-// written out of stream, microseconds after its neighbours, costs 11-19 % of the bandwidth because
-// its line has already left L2; written in stream it is free):
-//   for each run r, in order
-//     - if the run starts inside a sector, that sector (tail of run r-1 and earlier, head of run r
-//       and later) is gathered cooperatively, lane j <-> byte j, and leaves as one coalesced store;
-//     - then every whole sector inside the run, 128-bit stores, source re-phased by funnel shifts;
-//   finally the partial last sector (pseudo-run nr).  Bytes outside [Q_0, Q_nr) belong to the
-//   neighbouring tile / batch (another warp) and are never touched.
-// Everything that is uniform per run is computed ONCE, lane r <-> run r, into table B
-//   {x: dst offset of the first whole sector, y: #16-byte vectors | flags, z: src offset of that
-//    sector, w: Q_r}, so the run loop costs one broadcast 128-bit shared load plus the copy.
-#define RUN_HAS_BOUNDARY 0x40000000
-#define RUN_SIMPLE       0x20000000
-#define RUN_COUNT_MASK   0x00ffffff
-
-__device__ __forceinline__ int4 rtb_load(uint32_t a) {
-    int4 v;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void rtb_store(uint32_t a, int x, int y, int z, int w) {
-    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-
-template <int POLICY, int PACK>
-__device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32_t rtb_a, int nr,
-                                          uint8_t* __restrict__ base32, int lane, int debug)
-{
-    __syncwarp();
-    const int q_first = rt_load(rt_a).x, q_last = rt_load(rt_a + 8 * nr).x;
-    // ---- table B, lane-parallel
-    for (int r = lane; r <= nr; r += 32) {
-        const int2 er = rt_load(rt_a + 8 * r);
-        const int qn = r < nr ? rt_load(rt_a + 8 * (r + 1)).x : er.x;
-        const int qp = r > 0 ? rt_load(rt_a + 8 * (r - 1)).x : q_first;
-        const int W = er.x >> 5;
-        int flags = 0;
-        if ((er.x & 31) && !(r > 0 && (qp >> 5) == W && (qp & 31))) {        // first boundary inside sector W owns it
-            flags = RUN_HAS_BOUNDARY;
-            if ((r == 0 || qp <= (W << 5)) && (r == nr || qn >= (W << 5) + 32)) flags |= RUN_SIMPLE;
-        }
-        const int sa = (er.x + 31) >> 5, sb = qn >> 5;
-        const int nb = sb > sa ? (sb - sa) << 1 : 0;
-        rtb_store(rtb_a + 16 * r, sa << 5, nb | flags, er.y + ((sa << 5) - er.x), er.x);
-    }
-    __syncwarp();
-    // ---- the stream
-    int dA = 0;
-    for (int r = 0; r <= nr; ++r) {
-        const int4 t = rtb_load(rtb_a + 16 * r);                               // warp-uniform (broadcast)
-        const int dB = t.z - t.x;                                            // S_r - Q_r
-#ifdef GM2_EMIT_DEBUG
-        if ((t.y & RUN_HAS_BOUNDARY) && !(debug & 1)) {
-#else
-        if (t.y & RUN_HAS_BOUNDARY) {
-#endif
-            const int pos = (t.w & ~31) + lane;
-            if (pos >= q_first && pos < q_last) {
-                int src;
-                if (t.y & RUN_SIMPLE) {
-                    src = pos + (pos < t.w ? dA : dB);
-                } else {                                   // three or more runs meet in this sector
-                    int rr = r; int2 ec = rt_load(rt_a + 8 * rr);
-                    if (pos < ec.x) { do { --rr; ec = rt_load(rt_a + 8 * rr); } while (pos < ec.x); }
-                    else { int qn = rt_load(rt_a + 8 * (rr + 1)).x;
-                           while (pos >= qn) { ++rr; ec = rt_load(rt_a + 8 * rr); qn = rt_load(rt_a + 8 * (rr + 1)).x; } }
-                    src = ec.y + (pos - ec.x);
-                }
-                st8<POLICY>(base32 + pos, PACK == 2 ? base_at_2bit(tile_a, src) : lds8(tile_a + (uint32_t)src));
-            }
-        }
-        const int nb = t.y & RUN_COUNT_MASK;
-        if (nb > 0 && PACK == 2) {
-            // two-bit source: one (unaligned) 32-bit window per 16 output bases, expanded in registers
-            int bidx = t.z + 16 * lane;                                      // source base index of this lane's vector
-            uint8_t* d = base32 + t.x + 16 * lane;
-            const int sh = 2 * (t.z & 15);                                   // warp-uniform, loop-invariant
-#pragma unroll 1
-            for (int v = lane; v < nb; v += 32, bidx += 512, d += 512) {
-                const uint32_t wa = tile_a + (uint32_t)((bidx >> 4) << 2);
-                st128<POLICY>(d, expand16(__funnelshift_r(lds32(wa), lds32(wa + 4), sh)));
-            }
-        } else if (nb > 0) {
-            const int mis = t.z & 15;
-            const uint32_t qa = tile_a + (uint32_t)(t.z - mis) + 16u * lane;
-            uint8_t* d = base32 + t.x + 16 * lane;
-            const int sh = (mis & 3) * 8;
-#ifdef GM2_EMIT_DEBUG
-            if (debug & 6) {
-                if (debug & 4) { for (int v = lane; v < nb; v += 32, d += 512) st128<POLICY>(d, make_uint4(sh, mis, nb, r)); }
-                else { uint32_t q = qa, acc = 0; for (int v = lane; v < nb; v += 32, q += 512) { const uint4 tt = lds128(q); acc ^= tt.x ^ tt.w; }
-                       if (acc == 0x12345u) st128<POLICY>(d, make_uint4(acc, 0, 0, 0)); }
-            } else
-#endif
-            if (mis == 0) {
-                uint32_t q = qa;
-#pragma unroll 1
-                for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
-            } else {
-                switch (mis >> 2) {
-                case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
-                case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
-                case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
-                default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
-                }
-            }
-        }
-        dA = dB;
-    }
-    __syncwarp();
-}
-
-#define EMIT_FRONT_PAD 32
-#define EMIT_BACK_PAD  64
-
-template <int POLICY, int MIN_CTAS, int PACK>
-__global__ void __launch_bounds__(256, MIN_CTAS)
-k_emit(const EmitParams p)
-{
-    // dynamic shared memory: 16 B front pad | tile bytes | 32 B over-read pad | slot tables | per-warp run tables
-    extern __shared__ __align__(128) uint8_t dsm[];
-    __shared__ __align__(8) unsigned long long bar;
-
-    const int ntl = p.ntiles > 0 ? p.ntiles : 1;
-    const int tile = p.order ? (int)(blockIdx.x % ntl) : (int)(blockIdx.x / p.nbatch);
-    const int b = p.order ? (int)(blockIdx.x / ntl) : (int)(blockIdx.x - tile * p.nbatch);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const bool have_tile = p.ntiles > 0;
-    const int sl0 = have_tile ? __ldg(p.tile_slot + tile) : 0;
-    const int nslots = have_tile ? __ldg(p.tile_slot + tile + 1) - sl0 : 0;
-    const int nwords = nslots >> 5;
-    const int tile_base = tile * p.tile_bytes;
-
-    const uint32_t dsm_a = smem_u32(dsm);
-    const uint32_t tile_a = dsm_a + EMIT_FRONT_PAD;
-    const uint32_t len_a = tile_a + (uint32_t)p.tile_smem_bytes + EMIT_BACK_PAD;
-    const uint32_t src_a = len_a + 4u * (uint32_t)p.slot_cap;
-    const uint32_t rt_a = src_a + 4u * (uint32_t)p.slot_cap + (uint32_t)warp * (uint32_t)(p.rt_cap + 2) * 24u;   // table A (8 B) + table B (16 B) per entry
-    const uint32_t rtb_a = rt_a + (uint32_t)(p.rt_cap + 2) * 8u;
-    int32_t* sm_len = reinterpret_cast<int32_t*>(dsm + EMIT_FRONT_PAD + p.tile_smem_bytes + EMIT_BACK_PAD);
-    int32_t* sm_src = sm_len + p.slot_cap;
-    const bool slots_staged = nslots <= p.slot_cap;
-
-    if (have_tile) {
-        const uint32_t bar_a = smem_u32(&bar);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const uint32_t bytes = (uint32_t)p.tile_smem_bytes;
-            const uint8_t* src = p.seq + (size_t)tile * p.tile_smem_bytes;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(tile_a), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
-        }
-        if (slots_staged) {
-            for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
-                sm_len[i] = __ldg(p.slot_len + sl0 + i);
-                sm_src[i] = __ldg(p.slot_src + sl0 + i) - tile_base;
-            }
-        }
-        __syncthreads();                      // barrier init + slot tables visible to every thread
-        uint32_t done = 0;                    // wait for phase 0 of the mbarrier (the TMA's complete_tx)
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
-        }
-    }
-
-    const int64_t sb = p.s0 + (int64_t)b * p.batch;
-    const int64_t se = sb + p.batch < p.s1 ? sb + p.batch : p.s1;
-    const int last_tile = p.ntiles > 0 ? p.ntiles - 1 : 0;
-    const int64_t img0 = __ldg(p.rec_off + p.s0);
-    const uint32_t lt_mask = (1u << lane) - 1u;
-
-    // per-sample metadata is fetched one sample ahead: record offset, this tile's output offset,
-    // the sample's length (last tile only) and ALL kept-bit words of the tile in one coalesced load
-    int64_t m_roff = 0; int m_toff = 0; uint32_t m_words = 0u;
-    auto load_meta = [&](int64_t s) {
-        m_roff = __ldg(p.rec_off + s);
-        if (have_tile) {
-            m_toff = __ldg(p.tile_off + (size_t)s * p.ntiles + tile);
-            m_words = lane < nwords ? __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + lane) : 0u;
-        }
-    };
-    int64_t s = sb + warp;
-    if (s < se) load_meta(s);
-    while (s < se) {
-        const int64_t roff = m_roff; const int toff = m_toff; const uint32_t words = m_words;
-        const int64_t sn = s + nwarps;
-        if (sn < se) load_meta(sn);
-
-        uint8_t* rec = p.out + (roff - img0);
-        const unsigned long long num = (unsigned long long)(p.first_idx + s + 1);
-        const int nd = ndigits_u64(num);
-        const int hl = p.prefix.len + nd + 1;
-        if (tile == 0) {
-            for (int i = lane; i < hl; i += 32) {
-                char ch;
-                if (i < p.prefix.len) ch = p.prefix.text[i];
-                else if (i == hl - 1) ch = '\n';
-                else ch = (char)('0' + (int)((num / c_pow10[nd - 1 - (i - p.prefix.len)]) % 10ull));
-                rec[i] = (uint8_t)ch;
-            }
-        }
-        uint8_t* seqout = rec + hl;
-        if (have_tile) {
-            const int A = (int)((uintptr_t)seqout & 31u);
-            uint8_t* base32 = seqout - A;
-            asm volatile("" : "+l"(base32));                   // keep the 64-bit base in registers (no re-derivation per run)
-            int q = toff + A;
-            int nr = 0;
-            uint32_t carry = 0u;
-            for (int c = 0; ; ++c) {
-                const bool done = c >= nwords;
-                if (done || nr + 17 > p.rt_cap) {               // tile finished, or table full: emit what we have
-                    if (nr > 0) {
-                        if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                        emit_runs<POLICY, PACK>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
-                        nr = 0; carry = 0u;
-                    }
-                    if (done) break;
-                }
-                const uint32_t w = c < 32 ? __shfl_sync(FULL_MASK, words, c)
-                                          : __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + c);   // warp-uniform
-                int len, src;
-                if (slots_staged) { len = (int)lds32(len_a + 4u * (32 * c + lane)); src = (int)lds32(src_a + 4u * (32 * c + lane)); }
-                else { len = __ldg(p.slot_len + sl0 + 32 * c + lane); src = __ldg(p.slot_src + sl0 + 32 * c + lane) - tile_base; }
-                const int x = ((w >> lane) & 1u) ? len : 0;
-                const int incl = warp_incl_scan(x, lane);
-                const uint32_t starts = w & ~((w << 1) | carry);
-                carry = w >> 31;
-                if ((starts >> lane) & 1u) rt_store(rt_a + 8u * (nr + __popc(starts & lt_mask)), q + incl - x, src);
-                nr += __popc(starts);
-                q += __shfl_sync(FULL_MASK, incl, 31);
-            }
-        }
-        if (tile == last_tile && lane == 0) seqout[__ldg(p.lengths + s)] = (uint8_t)'\n';
-        s = sn;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// diagnostics
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_fill(uint4* __restrict__ dst, int64_t nvec, uint32_t pattern)
-{
-    const uint4 v = make_uint4(pattern, pattern, pattern, pattern);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) dst[i] = v;
-}
-
-// Store-only model of k_emit's write pattern: CTA = (tile, batch of samples), each warp streams
-// `chunk` contiguous bytes of record s at offset tile*chunk, records `stride` bytes apart.
-__global__ void __launch_bounds__(256)
-k_fill_streams(uint8_t* __restrict__ dst, int64_t nrec, int64_t stride, int ntile, int64_t chunk, int batch, int nbatch,
-               int order, int vec32)
-{
-    const int tile = order ? (int)(blockIdx.x % ntile) : (int)(blockIdx.x / nbatch);
-    const int b = order ? (int)(blockIdx.x / ntile) : (int)(blockIdx.x - tile * nbatch);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int64_t sb = (int64_t)b * batch, se = sb + batch < nrec ? sb + batch : nrec;
-    const uint4 v = make_uint4(0x41414141u, 0x43434343u, 0x47474747u, 0x54545454u);
-    for (int64_t s = sb + warp; s < se; s += nwarps) {
-        // vec32 bits: 1 = 256-bit stores; bits 8.. = misalignment of the chunk start in bytes (multiple of 32);
-        // bits 16.. = fragment length in bytes (0 = none): after every fragment 32 bytes are skipped,
-        // modelling a run boundary whose sector is written separately
-        const int mis = (vec32 >> 8) & 0xff, frag = vec32 >> 16;
-        uint8_t* p = dst + s * stride + (int64_t)tile * chunk + mis;
-        const int64_t n = chunk - mis;
-        if (frag) {
-            for (int64_t f0 = 0; f0 + frag <= n; f0 += frag) {
-                for (int64_t o = 16 * lane; o + 16 <= frag - 32; o += 512) *reinterpret_cast<uint4*>(p + f0 + o) = v;
-                if ((vec32 & 4) && lane == ((f0 / frag) & 31)) st256(p + f0 + frag - 32, v, v);     // in-stream, one lane
-                if ((vec32 & 8) && lane < 2) *reinterpret_cast<uint4*>(p + f0 + frag - 32 + 16 * lane) = v;   // in-stream, two lanes
-            }
-            if ((vec32 & 2)) {                                  // the skipped sectors, one lane each, afterwards
-                for (int64_t f0 = (int64_t)frag * (lane + 1) - 32; f0 + 32 <= n; f0 += (int64_t)frag * 32) st256(p + f0, v, v);
-            }
-        }
-        else if (vec32 & 1) { for (int64_t o = 32 * lane; o + 32 <= n; o += 1024) st256(p + o, v, v); }
-        else                { for (int64_t o = 16 * lane; o + 16 <= n; o += 512) *reinterpret_cast<uint4*>(p + o) = v; }
-    }
-}
-
-__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
-__device__ __forceinline__ void range_hash_block(const uint8_t* __restrict__ buf, int64_t buf_bytes, int64_t o0, int64_t n,
-                                                 unsigned long long* __restrict__ out_r)
-{
-    const int64_t nwords = (n + 7) >> 3;
-    const int m = (int)(o0 & 7);
-    const uint8_t* abase = buf + (o0 - m);                       // 8-byte aligned (buf is)
-    const unsigned long long* w64 = reinterpret_cast<const unsigned long long*>(abase);
-    const int64_t abytes = buf_bytes - (o0 - m);                // bytes readable from abase
-    const int64_t avail = abytes >> 3;                          // whole aligned words readable
-    auto load_word = [&](int64_t k) -> unsigned long long {
-        if (k < avail) return w64[k];
-        unsigned long long w = 0;                               // partial word at the buffer's end
-        for (int b = 0; b < 8; ++b) {
-            const int64_t p = 8 * k + b;
-            if (p < abytes) w |= (unsigned long long)abase[p] << (8 * b);
-        }
-        return w;
-    };
-    unsigned long long acc = 0;
-    for (int64_t k = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < nwords; k += (int64_t)gridDim.y * blockDim.x) {
-        unsigned long long w = load_word(k);
-        if (m) w = (w >> (8 * m)) | (load_word(k + 1) << (64 - 8 * m));
-        const int64_t valid = n - 8 * k;
-        if (valid < 8) w &= (1ull << (8 * valid)) - 1ull;
-        acc += mix64((unsigned long long)k * 0x9E3779B97F4A7C15ull + w);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, d);
-    __shared__ unsigned long long part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int i = 0; i < 8; ++i) t += part[i];
-        atomicAdd(out_r, t);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_range_hashes(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t* __restrict__ off,
-               unsigned long long* __restrict__ out)
-{
-    const int64_t r = blockIdx.x;
-    range_hash_block(buf, buf_bytes, off[r], off[r + 1] - off[r], out + r);
-}
-
-// same, ranges given as (begin, end) pairs
-__global__ void __launch_bounds__(256)
-k_range_hashes_pairs(const uint8_t* __restrict__ buf, int64_t buf_bytes, const int64_t* __restrict__ pairs,
-                     unsigned long long* __restrict__ out)
-{
-    const int64_t r = blockIdx.x;
-    range_hash_block(buf, buf_bytes, pairs[2 * r], pairs[2 * r + 1] - pairs[2 * r], out + r);
-}
-
 
 // ------------------------------------------------------------------------------------------
 // C-ABI
@@ -1767,3 +910,4 @@ GM2_API int gm2_diag_range_hashes(gm2_ctx* c, const uint8_t* dev, int64_t dev_by
     cudaFree(d_off); cudaFree(d_out);
     return rc;
 }
+

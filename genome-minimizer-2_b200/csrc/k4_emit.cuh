@@ -1,0 +1,399 @@
+// k4_emit.cuh — part of libgm2.so (included by gm2.cu; one translation unit).
+// K4: TMA-staged stream-compaction gather with fused FASTA framing (k_emit).
+#pragma once
+
+#include "device_util.cuh"
+
+#define GM2_MAX_PREFIX 95
+
+struct HeaderPrefix {            // passed by value to kernels; text[0] is '>'
+    int  len;
+    char text[GM2_MAX_PREFIX + 1];
+};
+
+
+// ------------------------------------------------------------------------------------------
+// K4  emit: stream-compaction gather + FASTA framing              (minimizer_2.py:94-97, :476-477)
+//   CTA = (genome tile, batch of samples).  The tile's bases are staged ONCE in shared
+//   memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and reused by every sample
+//   of the batch.  Each warp owns one sample at a time: it reads the tile's kept-bit
+//   words, scans kept segment lengths with shuffles, and copies every maximal kept run
+//   shared->global with destination-aligned 128-bit stores (the source is re-phased with
+//   funnel shifts); only a run's <16-byte head and tail use byte stores.  The warp that
+//   owns tile 0 writes the '>' header, the one that owns the last tile the final '\n'.
+// ------------------------------------------------------------------------------------------
+struct EmitParams {
+    const uint8_t* seq;
+    const int32_t* tile_slot;
+    const int32_t* slot_src;
+    const int32_t* slot_len;
+    const uint32_t* segkept;
+    const int32_t* tile_off;
+    const int64_t* lengths;
+    const int64_t* rec_off;
+    uint8_t* out;
+    int64_t s0, s1;
+    int64_t first_idx;
+    int tile_bytes, ntiles, SW, batch, nbatch;
+    int tile_smem_bytes;   // bytes of the staged tile: tile_bytes (1 byte/base) or tile_bytes/4 (2 bits/base)
+    int rt_cap;            // run-table entries per warp (shared memory)
+    int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
+    int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
+    int debug;             // timing experiments only (wrong output; needs -DGM2_EMIT_DEBUG): 1 no boundary
+                           // sectors, 2 no interior stores, 4 interior stores without shared loads
+    HeaderPrefix prefix;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// shared-memory accessors on 32-bit shared-window addresses.  Tile / slot-table reads are plain
+// (read-only after the CTA barrier, free to be scheduled); run-table accesses are volatile with a
+// memory clobber because the table is rewritten per (sample, tile) around __syncwarp().
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 rt_load(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rt_store(uint32_t a, int x, int y) {
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void rt_store_x(uint32_t a, int x) {
+    asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(x) : "memory");
+}
+
+// POLICY 1 = streaming (evict-first) stores: the image is written once and never re-read here.
+template <int POLICY>
+__device__ __forceinline__ void st128(uint8_t* p, const uint4& v) {
+    if (POLICY == 1) __stcs(reinterpret_cast<uint4*>(p), v);
+    else *reinterpret_cast<uint4*>(p) = v;
+}
+template <int POLICY>
+__device__ __forceinline__ void st8(uint8_t* p, uint32_t v) {
+    if (POLICY == 1) __stcs(p, (uint8_t)v);
+    else *p = (uint8_t)v;
+}
+
+// One whole 32-byte sector from one lane (STG.256).
+__device__ __forceinline__ void st256(uint8_t* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// ---- 2-bit packing (ACGT-only references): base i of the tile sits in bits [2i, 2i+2) of the
+// little-endian bit stream, code 0..3 = A, C, G, T.  Sixteen bases = one 32-bit word.
+#define ACGT_LUT 0x54474341u                     // 'A' 'C' 'G' 'T' as bytes 0..3
+__device__ __forceinline__ uint32_t spread8(uint32_t t) {      // 8 two-bit codes -> 8 nibbles
+    t &= 0xffffu;
+    t = (t | (t << 8)) & 0x00ff00ffu;
+    t = (t | (t << 4)) & 0x0f0f0f0fu;
+    t = (t | (t << 2)) & 0x33333333u;
+    return t;
+}
+__device__ __forceinline__ uint4 expand16(uint32_t x) {       // 16 codes -> 16 ASCII bytes (PRMT as a 4-entry LUT)
+    const uint32_t lo = spread8(x), hi = spread8(x >> 16);
+    return make_uint4(__byte_perm(ACGT_LUT, 0u, lo), __byte_perm(ACGT_LUT, 0u, lo >> 16),
+                      __byte_perm(ACGT_LUT, 0u, hi), __byte_perm(ACGT_LUT, 0u, hi >> 16));
+}
+__device__ __forceinline__ uint32_t base_at_2bit(uint32_t tile_a, int b) {
+    const uint32_t w = lds32(tile_a + (uint32_t)((b >> 4) << 2));
+    return (ACGT_LUT >> (8u * ((w >> (2 * (b & 15))) & 3u))) & 0xffu;
+}
+
+// Interior of one kept run: nb destination-aligned 16-byte vectors, lanes strided by 32.
+// qa = this lane's 16-byte aligned shared address at or below its first source byte,
+// K = word phase (0..3), sh = byte phase in bits.
+template <int POLICY, int K>
+__device__ __forceinline__ void copy_vectors(uint32_t qa, uint8_t* __restrict__ d, int nb, int sh, int lane)
+{
+#pragma unroll 1
+    for (int v = lane; v < nb; v += 32, qa += 512, d += 512) {
+        const uint4 lo = lds128(qa);
+        const uint4 hi = lds128(qa + 16);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        uint4 o;
+        o.x = __funnelshift_r(w[K], w[K + 1], sh);
+        o.y = __funnelshift_r(w[K + 1], w[K + 2], sh);
+        o.z = __funnelshift_r(w[K + 2], w[K + 3], sh);
+        o.w = __funnelshift_r(w[K + 3], w[K + 4], sh);
+        st128<POLICY>(d, o);
+    }
+}
+
+// 16 bytes from an arbitrarily aligned shared address (per-lane alignment).
+__device__ __forceinline__ uint4 fetch16(uint32_t a) {
+    const uint32_t a4 = a & ~3u;
+    const int sh = (int)(a & 3u) * 8;
+    const uint32_t w0 = lds32(a4), w1 = lds32(a4 + 4), w2 = lds32(a4 + 8), w3 = lds32(a4 + 12), w4 = lds32(a4 + 16);
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                      __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+__device__ __forceinline__ uint32_t low_bytes_mask(int n) {          // n bytes from the low end, n clamped to 0..4
+    return n >= 4 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
+}
+
+// One batch of kept runs of a (sample, tile): table A entry r = {Q_r, S_r}, entry nr = {end, -}.
+//   Q = destination offset in "Q space" (bytes from base32, a 32-byte aligned global pointer),
+//   S = source byte offset inside the shared-memory tile.  Output is contiguous: run r covers
+//   [Q_r, Q_{r+1}).
+// The warp writes ONE ASCENDING STREAM in units of 32-byte sectors, each sector exactly once and
+// in address order (measured with store-only models, profiles/r01_emit_experiments.md: a sector
+// written out of stream, microseconds after its neighbours, costs 11-19 % of the bandwidth because
+// its line has already left L2; written in stream it is free):
+//   for each run r, in order
+//     - if the run starts inside a sector, that sector (tail of run r-1 and earlier, head of run r
+//       and later) is gathered cooperatively, lane j <-> byte j, and leaves as one coalesced store;
+//     - then every whole sector inside the run, 128-bit stores, source re-phased by funnel shifts;
+//   finally the partial last sector (pseudo-run nr).  Bytes outside [Q_0, Q_nr) belong to the
+//   neighbouring tile / batch (another warp) and are never touched.
+// Everything that is uniform per run is computed ONCE, lane r <-> run r, into table B
+//   {x: dst offset of the first whole sector, y: #16-byte vectors | flags, z: src offset of that
+//    sector, w: Q_r}, so the run loop costs one broadcast 128-bit shared load plus the copy.
+#define RUN_HAS_BOUNDARY 0x40000000
+#define RUN_SIMPLE       0x20000000
+#define RUN_COUNT_MASK   0x00ffffff
+
+__device__ __forceinline__ int4 rtb_load(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rtb_store(uint32_t a, int x, int y, int z, int w) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+template <int POLICY, int PACK>
+__device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32_t rtb_a, int nr,
+                                          uint8_t* __restrict__ base32, int lane, int debug)
+{
+    __syncwarp();
+    const int q_first = rt_load(rt_a).x, q_last = rt_load(rt_a + 8 * nr).x;
+    // ---- table B, lane-parallel
+    for (int r = lane; r <= nr; r += 32) {
+        const int2 er = rt_load(rt_a + 8 * r);
+        const int qn = r < nr ? rt_load(rt_a + 8 * (r + 1)).x : er.x;
+        const int qp = r > 0 ? rt_load(rt_a + 8 * (r - 1)).x : q_first;
+        const int W = er.x >> 5;
+        int flags = 0;
+        if ((er.x & 31) && !(r > 0 && (qp >> 5) == W && (qp & 31))) {        // first boundary inside sector W owns it
+            flags = RUN_HAS_BOUNDARY;
+            if ((r == 0 || qp <= (W << 5)) && (r == nr || qn >= (W << 5) + 32)) flags |= RUN_SIMPLE;
+        }
+        const int sa = (er.x + 31) >> 5, sb = qn >> 5;
+        const int nb = sb > sa ? (sb - sa) << 1 : 0;
+        rtb_store(rtb_a + 16 * r, sa << 5, nb | flags, er.y + ((sa << 5) - er.x), er.x);
+    }
+    __syncwarp();
+    // ---- the stream
+    int dA = 0;
+    for (int r = 0; r <= nr; ++r) {
+        const int4 t = rtb_load(rtb_a + 16 * r);                               // warp-uniform (broadcast)
+        const int dB = t.z - t.x;                                            // S_r - Q_r
+#ifdef GM2_EMIT_DEBUG
+        if ((t.y & RUN_HAS_BOUNDARY) && !(debug & 1)) {
+#else
+        if (t.y & RUN_HAS_BOUNDARY) {
+#endif
+            const int pos = (t.w & ~31) + lane;
+            if (pos >= q_first && pos < q_last) {
+                int src;
+                if (t.y & RUN_SIMPLE) {
+                    src = pos + (pos < t.w ? dA : dB);
+                } else {                                   // three or more runs meet in this sector
+                    int rr = r; int2 ec = rt_load(rt_a + 8 * rr);
+                    if (pos < ec.x) { do { --rr; ec = rt_load(rt_a + 8 * rr); } while (pos < ec.x); }
+                    else { int qn = rt_load(rt_a + 8 * (rr + 1)).x;
+                           while (pos >= qn) { ++rr; ec = rt_load(rt_a + 8 * rr); qn = rt_load(rt_a + 8 * (rr + 1)).x; } }
+                    src = ec.y + (pos - ec.x);
+                }
+                st8<POLICY>(base32 + pos, PACK == 2 ? base_at_2bit(tile_a, src) : lds8(tile_a + (uint32_t)src));
+            }
+        }
+        const int nb = t.y & RUN_COUNT_MASK;
+        if (nb > 0 && PACK == 2) {
+            // two-bit source: one (unaligned) 32-bit window per 16 output bases, expanded in registers
+            int bidx = t.z + 16 * lane;                                      // source base index of this lane's vector
+            uint8_t* d = base32 + t.x + 16 * lane;
+            const int sh = 2 * (t.z & 15);                                   // warp-uniform, loop-invariant
+#pragma unroll 1
+            for (int v = lane; v < nb; v += 32, bidx += 512, d += 512) {
+                const uint32_t wa = tile_a + (uint32_t)((bidx >> 4) << 2);
+                st128<POLICY>(d, expand16(__funnelshift_r(lds32(wa), lds32(wa + 4), sh)));
+            }
+        } else if (nb > 0) {
+            const int mis = t.z & 15;
+            const uint32_t qa = tile_a + (uint32_t)(t.z - mis) + 16u * lane;
+            uint8_t* d = base32 + t.x + 16 * lane;
+            const int sh = (mis & 3) * 8;
+#ifdef GM2_EMIT_DEBUG
+            if (debug & 6) {
+                if (debug & 4) { for (int v = lane; v < nb; v += 32, d += 512) st128<POLICY>(d, make_uint4(sh, mis, nb, r)); }
+                else { uint32_t q = qa, acc = 0; for (int v = lane; v < nb; v += 32, q += 512) { const uint4 tt = lds128(q); acc ^= tt.x ^ tt.w; }
+                       if (acc == 0x12345u) st128<POLICY>(d, make_uint4(acc, 0, 0, 0)); }
+            } else
+#endif
+            if (mis == 0) {
+                uint32_t q = qa;
+#pragma unroll 1
+                for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
+            } else {
+                switch (mis >> 2) {
+                case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
+                case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
+                case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
+                default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
+                }
+            }
+        }
+        dA = dB;
+    }
+    __syncwarp();
+}
+
+#define EMIT_FRONT_PAD 32
+#define EMIT_BACK_PAD  64
+
+template <int POLICY, int MIN_CTAS, int PACK>
+__global__ void __launch_bounds__(256, MIN_CTAS)
+k_emit(const EmitParams p)
+{
+    // dynamic shared memory: 16 B front pad | tile bytes | 32 B over-read pad | slot tables | per-warp run tables
+    extern __shared__ __align__(128) uint8_t dsm[];
+    __shared__ __align__(8) unsigned long long bar;
+
+    const int ntl = p.ntiles > 0 ? p.ntiles : 1;
+    const int tile = p.order ? (int)(blockIdx.x % ntl) : (int)(blockIdx.x / p.nbatch);
+    const int b = p.order ? (int)(blockIdx.x / ntl) : (int)(blockIdx.x - tile * p.nbatch);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const bool have_tile = p.ntiles > 0;
+    const int sl0 = have_tile ? __ldg(p.tile_slot + tile) : 0;
+    const int nslots = have_tile ? __ldg(p.tile_slot + tile + 1) - sl0 : 0;
+    const int nwords = nslots >> 5;
+    const int tile_base = tile * p.tile_bytes;
+
+    const uint32_t dsm_a = smem_u32(dsm);
+    const uint32_t tile_a = dsm_a + EMIT_FRONT_PAD;
+    const uint32_t len_a = tile_a + (uint32_t)p.tile_smem_bytes + EMIT_BACK_PAD;
+    const uint32_t src_a = len_a + 4u * (uint32_t)p.slot_cap;
+    const uint32_t rt_a = src_a + 4u * (uint32_t)p.slot_cap + (uint32_t)warp * (uint32_t)(p.rt_cap + 2) * 24u;   // table A (8 B) + table B (16 B) per entry
+    const uint32_t rtb_a = rt_a + (uint32_t)(p.rt_cap + 2) * 8u;
+    int32_t* sm_len = reinterpret_cast<int32_t*>(dsm + EMIT_FRONT_PAD + p.tile_smem_bytes + EMIT_BACK_PAD);
+    int32_t* sm_src = sm_len + p.slot_cap;
+    const bool slots_staged = nslots <= p.slot_cap;
+
+    if (have_tile) {
+        const uint32_t bar_a = smem_u32(&bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = (uint32_t)p.tile_smem_bytes;
+            const uint8_t* src = p.seq + (size_t)tile * p.tile_smem_bytes;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(tile_a), "l"(src), "r"(bytes), "r"(bar_a) : "memory");
+        }
+        if (slots_staged) {
+            for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+                sm_len[i] = __ldg(p.slot_len + sl0 + i);
+                sm_src[i] = __ldg(p.slot_src + sl0 + i) - tile_base;
+            }
+        }
+        __syncthreads();                      // barrier init + slot tables visible to every thread
+        uint32_t done = 0;                    // wait for phase 0 of the mbarrier (the TMA's complete_tx)
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+        }
+    }
+
+    const int64_t sb = p.s0 + (int64_t)b * p.batch;
+    const int64_t se = sb + p.batch < p.s1 ? sb + p.batch : p.s1;
+    const int last_tile = p.ntiles > 0 ? p.ntiles - 1 : 0;
+    const int64_t img0 = __ldg(p.rec_off + p.s0);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // per-sample metadata is fetched one sample ahead: record offset, this tile's output offset,
+    // the sample's length (last tile only) and ALL kept-bit words of the tile in one coalesced load
+    int64_t m_roff = 0; int m_toff = 0; uint32_t m_words = 0u;
+    auto load_meta = [&](int64_t s) {
+        m_roff = __ldg(p.rec_off + s);
+        if (have_tile) {
+            m_toff = __ldg(p.tile_off + (size_t)s * p.ntiles + tile);
+            m_words = lane < nwords ? __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + lane) : 0u;
+        }
+    };
+    int64_t s = sb + warp;
+    if (s < se) load_meta(s);
+    while (s < se) {
+        const int64_t roff = m_roff; const int toff = m_toff; const uint32_t words = m_words;
+        const int64_t sn = s + nwarps;
+        if (sn < se) load_meta(sn);
+
+        uint8_t* rec = p.out + (roff - img0);
+        const unsigned long long num = (unsigned long long)(p.first_idx + s + 1);
+        const int nd = ndigits_u64(num);
+        const int hl = p.prefix.len + nd + 1;
+        if (tile == 0) {
+            for (int i = lane; i < hl; i += 32) {
+                char ch;
+                if (i < p.prefix.len) ch = p.prefix.text[i];
+                else if (i == hl - 1) ch = '\n';
+                else ch = (char)('0' + (int)((num / c_pow10[nd - 1 - (i - p.prefix.len)]) % 10ull));
+                rec[i] = (uint8_t)ch;
+            }
+        }
+        uint8_t* seqout = rec + hl;
+        if (have_tile) {
+            const int A = (int)((uintptr_t)seqout & 31u);
+            uint8_t* base32 = seqout - A;
+            asm volatile("" : "+l"(base32));                   // keep the 64-bit base in registers (no re-derivation per run)
+            int q = toff + A;
+            int nr = 0;
+            uint32_t carry = 0u;
+            for (int c = 0; ; ++c) {
+                const bool done = c >= nwords;
+                if (done || nr + 17 > p.rt_cap) {               // tile finished, or table full: emit what we have
+                    if (nr > 0) {
+                        if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
+                        emit_runs<POLICY, PACK>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
+                        nr = 0; carry = 0u;
+                    }
+                    if (done) break;
+                }
+                const uint32_t w = c < 32 ? __shfl_sync(FULL_MASK, words, c)
+                                          : __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + c);   // warp-uniform
+                int len, src;
+                if (slots_staged) { len = (int)lds32(len_a + 4u * (32 * c + lane)); src = (int)lds32(src_a + 4u * (32 * c + lane)); }
+                else { len = __ldg(p.slot_len + sl0 + 32 * c + lane); src = __ldg(p.slot_src + sl0 + 32 * c + lane) - tile_base; }
+                const int x = ((w >> lane) & 1u) ? len : 0;
+                const int incl = warp_incl_scan(x, lane);
+                const uint32_t starts = w & ~((w << 1) | carry);
+                carry = w >> 31;
+                if ((starts >> lane) & 1u) rt_store(rt_a + 8u * (nr + __popc(starts & lt_mask)), q + incl - x, src);
+                nr += __popc(starts);
+                q += __shfl_sync(FULL_MASK, incl, 31);
+            }
+        }
+        if (tile == last_tile && lane == 0) seqout[__ldg(p.lengths + s)] = (uint8_t)'\n';
+        s = sn;
+    }
+}
+
