@@ -273,7 +273,7 @@ template <int POLICY, int MIN_CTAS, int PACK>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 k_emit(const EmitParams p)
 {
-    // dynamic shared memory: 16 B front pad | tile bytes | 32 B over-read pad | slot tables | per-warp run tables
+    // dynamic shared memory: 32 B front pad | staged tile | 64 B over-read pad | slot tables | per-warp run tables A + B
     extern __shared__ __align__(128) uint8_t dsm[];
     __shared__ __align__(8) unsigned long long bar;
 
