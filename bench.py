@@ -203,6 +203,27 @@ def cpu_literal_single_thread(g, table, keep_names, noise_ids, n):
     return bases / dt / 1e9, dt, bases
 
 
+def cpu_c_port_all_cores(g, table, keep_names, n):
+    """For context only: the oracle's optimised C restatement (difference array + one pass) threaded
+    over all host cores — a far stronger CPU program than the reference's Python loop."""
+    from concurrent.futures import ThreadPoolExecutor
+    from genome_minimizer_2_b200 import synth
+    from oracle import c_oracle
+    starts, ends = g.starts_ends()
+    name_id = np.asarray([table.name_to_id[x] for x in table.names])
+    n = min(n, keep_names.shape[0])
+    rows = synth.pack_keep_rows(keep_names[:n][:, name_id])
+    c_oracle.lib()
+    cores = os.cpu_count() or 1
+    chunks = [(a, min(a + 4, n)) for a in range(0, n, 4)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        bases = sum(int(L.sum()) for L in ex.map(lambda ab: c_oracle.batch(g.seq, starts, ends, rows[ab[0]:ab[1]], first_idx=ab[0])[0], chunks))
+    dt = time.perf_counter() - t0
+    return {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port (optimised C, not the reference's algorithmic cost)",
+            "sample": f"first {n} samples of the workload, oracle/minimizer_c.c threaded over {cores} cores, records hashed, {dt:.2f} s"}
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's CPU algorithm (oracle literal port; the reference is
     pure Python and cannot travel to the GPU box) over all host cores, bounded sample per step."""
@@ -556,6 +577,10 @@ def main():
                                   f"minimizer_2.py:50-101 (list scan + position set + per-base loop), {dt:.1f} s",
                         "host_cores_available": os.cpu_count()}
 
+    cpu_c = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_c = cpu_c_port_all_cores(g, table, keep_names, 8 * (os.cpu_count() or 1))
+
     dropin = None
     if world == 1 and not args.no_dropin:
         dropin = dropin_c1(g, table, args)
@@ -571,7 +596,7 @@ def main():
                    "sharding": "samples; reference replicated; all-gather of image sizes only",
                    "tile_bytes": args.tile_bytes or 49152, "kept_bases_per_gpu": kept_bases},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "verify": verify, "dropin_c1": dropin,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_port_c": cpu_c, "verify": verify, "dropin_c1": dropin,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
