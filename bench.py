@@ -579,7 +579,7 @@ def main():
 
     cpu_c = None
     if not args.no_cpu_baseline and world == 1:
-        cpu_c = cpu_c_port_all_cores(g, table, keep_names, 8 * (os.cpu_count() or 1))
+        cpu_c = cpu_c_port_all_cores(g, table, keep_names, 32 * (os.cpu_count() or 1))
 
     dropin = None
     if world == 1 and not args.no_dropin:
