@@ -585,17 +585,11 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;
         keep = c->own_keep;
         if (S > 0 && c->FW > 0) {
-            const size_t rows_b = (size_t)K1_WARPS * c->FW * 4;
-            const size_t map_b = ((size_t)c->V + (size_t)c->F) * 4;
-            const int map_in_smem = rows_b + map_b <= 96 * 1024;
-            const size_t sm = rows_b + (map_in_smem ? map_b : 0);
+            const size_t sm = (size_t)c->FW * 4;
             if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: too many genes for the keep-row staging buffer");
-            CU(c, cudaFuncSetAttribute(k_keep_from_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            const int64_t groups = (S + K1_WARPS - 1) / K1_WARPS;
-            const int64_t blocks = std::min<int64_t>(groups, (int64_t)c->sm_count * (map_in_smem ? 4 : 8));
-            k_keep_from_ids<<<(unsigned)blocks, K1_WARPS * 32, sm, c->stream>>>(c->ids, c->ids_off, S, c->V, c->F,
-                                                                              c->d_first_gene, c->d_next_same, c->FW,
-                                                                              c->own_keep, map_in_smem);
+            if (sm > 48 * 1024) CU(c, cudaFuncSetAttribute(k_keep_from_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_keep_from_ids<<<(unsigned)S, K1_THREADS, sm, c->stream>>>(c->ids, c->ids_off, S, c->V, c->d_first_gene,
+                                                                        c->d_next_same, c->FW, c->own_keep);
             LAUNCH_CHECK(c, "k_keep_from_ids");
         }
     }

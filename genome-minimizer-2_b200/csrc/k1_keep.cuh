@@ -6,60 +6,47 @@
 
 // ------------------------------------------------------------------------------------------
 // K1  keep-mask builder: name-id lists -> F-bit keep rows          (minimizer_2.py:59-63)
-//   One warp per sample, CTAs loop over groups of samples.  The static name table is a
-//   linked list through the genes (first_gene[id] -> next_same_name[g] -> ...), staged in
-//   shared memory when it fits, so an id costs one coalesced global load plus shared-memory
-//   lookups; the row is assembled in shared memory with atomicOr and written out coalesced.
+//   One CTA per sample: every thread takes 128-bit vectors of the sample's id list (all of them
+//   in flight at once), walks the static name table — a linked list through the genes,
+//   first_gene[id] -> next_same_name[g] -> ..., a few KB that stay in L1 — and sets bits in the
+//   sample's row in shared memory with atomicOr; the row is written out coalesced.  (A warp per
+//   sample with the table staged in shared memory measured 3x slower: with ~2 samples per
+//   resident warp the kernel ran for three whole sample latencies.)
 // ------------------------------------------------------------------------------------------
-#define K1_WARPS 8
-__global__ void __launch_bounds__(K1_WARPS * 32, 4)
-k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V, int32_t F,
+#define K1_THREADS 256
+__global__ void __launch_bounds__(K1_THREADS)
+k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V,
                 const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
-                int FW, uint32_t* __restrict__ keep, int map_in_smem)
+                int FW, uint32_t* __restrict__ keep)
 {
-    extern __shared__ uint32_t k1_sm[];
-    uint32_t* rows = k1_sm;                                          // K1_WARPS x FW
-    const int32_t* fg = first_gene;
-    const int32_t* nx = next_same;
-    if (map_in_smem) {
-        int32_t* s_fg = reinterpret_cast<int32_t*>(k1_sm + (size_t)K1_WARPS * FW);
-        int32_t* s_nx = s_fg + V;
-        for (int i = threadIdx.x; i < V; i += blockDim.x) s_fg[i] = first_gene[i];
-        for (int i = threadIdx.x; i < F; i += blockDim.x) s_nx[i] = next_same[i];
-        fg = s_fg; nx = s_nx;
-        __syncthreads();
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* row = rows + (size_t)warp * FW;
-    for (int64_t s = (int64_t)blockIdx.x * K1_WARPS + warp; s < S; s += (int64_t)gridDim.x * K1_WARPS) {
-        for (int i = lane; i < FW; i += 32) row[i] = 0u;
-        __syncwarp();
-        const int64_t b = off[s], e = off[s + 1];
-        auto mark = [&](int32_t id) {
-            if ((uint32_t)id < (uint32_t)V)
-                for (int g = fg[id]; g >= 0; g = nx[g]) atomicOr(&row[g >> 5], 1u << (g & 31));
-        };
-        // head up to a 16-byte boundary, 128-bit body (two vectors per lane in flight), scalar tail
-        const int64_t b4 = min((b + 3) & ~(int64_t)3, e), e4 = b4 + ((e - b4) & ~(int64_t)3);
-        if (b + lane < b4) mark(__ldg(ids + b + lane));
-        const int4* v4 = reinterpret_cast<const int4*>(ids + b4);
-        const int64_t nv = (e4 - b4) >> 2;
-        for (int64_t i0 = 0; i0 < nv; i0 += 128) {
-            int4 x[4];
+    extern __shared__ uint32_t k1_row[];
+    const int64_t s = blockIdx.x;
+    for (int i = threadIdx.x; i < FW; i += blockDim.x) k1_row[i] = 0u;
+    __syncthreads();
+    const int64_t b = off[s], e = off[s + 1];
+    auto mark = [&](int32_t id) {
+        if ((uint32_t)id < (uint32_t)V)
+            for (int g = __ldg(first_gene + id); g >= 0; g = __ldg(next_same + g)) atomicOr(&k1_row[g >> 5], 1u << (g & 31));
+    };
+    // head up to a 16-byte boundary, 128-bit body, scalar tail
+    const int64_t b4 = min((b + 3) & ~(int64_t)3, e), e4 = b4 + ((e - b4) & ~(int64_t)3);
+    if (b + threadIdx.x < b4) mark(__ldg(ids + b + threadIdx.x));
+    const int4* v4 = reinterpret_cast<const int4*>(ids + b4);
+    const int64_t nv = (e4 - b4) >> 2;
+    for (int64_t i0 = 0; i0 < nv; i0 += 4 * K1_THREADS) {
+        int4 x[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + 32 * u + lane;
-                x[u] = i < nv ? __ldg(v4 + i) : make_int4(-1, -1, -1, -1);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { mark(x[u].x); mark(x[u].y); mark(x[u].z); mark(x[u].w); }
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + (int64_t)u * K1_THREADS + threadIdx.x;
+            x[u] = i < nv ? __ldg(v4 + i) : make_int4(-1, -1, -1, -1);
         }
-        if (e4 + lane < e) mark(__ldg(ids + e4 + lane));
-        __syncwarp();
-        uint32_t* dst = keep + (size_t)s * FW;
-        for (int i = lane; i < FW; i += 32) dst[i] = row[i];
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { mark(x[u].x); mark(x[u].y); mark(x[u].z); mark(x[u].w); }
     }
+    if (e4 + threadIdx.x < e) mark(__ldg(ids + e4 + threadIdx.x));
+    __syncthreads();
+    uint32_t* dst = keep + (size_t)s * FW;
+    for (int i = threadIdx.x; i < FW; i += blockDim.x) dst[i] = k1_row[i];
 }
 
 // ------------------------------------------------------------------------------------------
