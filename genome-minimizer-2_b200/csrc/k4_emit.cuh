@@ -14,13 +14,13 @@ struct HeaderPrefix {            // passed by value to kernels; text[0] is '>'
 
 // ------------------------------------------------------------------------------------------
 // K4  emit: stream-compaction gather + FASTA framing              (minimizer_2.py:94-97, :476-477)
-//   CTA = (genome tile, batch of samples).  The tile's bases are staged ONCE in shared
-//   memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and reused by every sample
-//   of the batch.  Each warp owns one sample at a time: it reads the tile's kept-bit
-//   words, scans kept segment lengths with shuffles, and copies every maximal kept run
-//   shared->global with destination-aligned 128-bit stores (the source is re-phased with
-//   funnel shifts); only a run's <16-byte head and tail use byte stores.  The warp that
-//   owns tile 0 writes the '>' header, the one that owns the last tile the final '\n'.
+//   CTA = (genome tile, batch of samples).  The tile's bases are staged ONCE in shared memory by a
+//   1-D TMA bulk copy (cp.async.bulk + mbarrier) and reused by every sample of the batch; the tile's
+//   static slot tables are staged beside it.  Each warp owns one sample at a time (the next sample's
+//   metadata is prefetched): it turns the tile's kept-bit words into a table of kept runs with
+//   shuffle scans, derives every per-run constant lane-parallel into a second table, and then writes
+//   the runs as one ascending stream of 32-byte sectors — see emit_runs.  The warp that owns tile 0
+//   writes the '>' header, the one that owns the last tile the final '\n'.
 // ------------------------------------------------------------------------------------------
 struct EmitParams {
     const uint8_t* seq;
@@ -48,22 +48,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// shared-memory accessors on 32-bit shared-window addresses.  Tile / slot-table reads are plain
-// (read-only after the CTA barrier, free to be scheduled); run-table accesses are volatile with a
-// memory clobber because the table is rewritten per (sample, tile) around __syncwarp().
+// shared-memory accessors on 32-bit shared-window addresses.  Tile / slot-table reads are `volatile`
+// asm WITHOUT a memory clobber: that keeps them behind the __syncthreads() / mbarrier wait that
+// publishes the staged data (a plain asm has no memory dependency the compiler would respect) while
+// leaving ptxas free to schedule them; run-table accesses add the memory clobber because the table
+// is rewritten per (sample, tile) around __syncwarp().
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) {
     uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ int2 rt_load(uint32_t a) {
@@ -134,18 +136,6 @@ __device__ __forceinline__ void copy_vectors(uint32_t qa, uint8_t* __restrict__ 
         o.w = __funnelshift_r(w[K + 3], w[K + 4], sh);
         st128<POLICY>(d, o);
     }
-}
-
-// 16 bytes from an arbitrarily aligned shared address (per-lane alignment).
-__device__ __forceinline__ uint4 fetch16(uint32_t a) {
-    const uint32_t a4 = a & ~3u;
-    const int sh = (int)(a & 3u) * 8;
-    const uint32_t w0 = lds32(a4), w1 = lds32(a4 + 4), w2 = lds32(a4 + 8), w3 = lds32(a4 + 12), w4 = lds32(a4 + 16);
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                      __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-__device__ __forceinline__ uint32_t low_bytes_mask(int n) {          // n bytes from the low end, n clamped to 0..4
-    return n >= 4 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (8 * n)) - 1u));
 }
 
 // One batch of kept runs of a (sample, tile): table A entry r = {Q_r, S_r}, entry nr = {end, -}.
