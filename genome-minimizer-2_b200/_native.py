@@ -55,6 +55,9 @@ SIGNATURES = {
     "gm2_emit_host": (_c.c_int, [_P, _I64, _I64, _P, _I64, _I64]),
     "gm2_sequence_hashes": (_c.c_int, [_P, _I64, _I64, _P]),
     "gm2_minimize_host": (_c.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64]),
+    "gm2_device_alloc": (_c.c_int, [_P, _c.POINTER(_P), _I64]),
+    "gm2_device_free": (_c.c_int, [_P, _P]),
+    "gm2_upload": (_c.c_int, [_P, _P, _P, _I64]),
     "gm2_host_alloc": (_c.c_int, [_c.POINTER(_P), _I64]),
     "gm2_host_free": (_c.c_int, [_P]),
     "gm2_diag_fill": (_c.c_int, [_P, _P, _I64, _c.c_uint32]),
@@ -313,6 +316,18 @@ class Context:
         out = np.zeros(s1 - s0, dtype=np.uint64)
         self._ck(self._lib.gm2_sequence_hashes(self._h, int(s0), int(s1), _ptr(out)))
         return out
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = _P()
+        self._ck(self._lib.gm2_device_alloc(self._h, ctypes.byref(p), int(nbytes)))
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        self._ck(self._lib.gm2_device_free(self._h, int(ptr)))
+
+    def upload(self, dev_ptr: int, host: np.ndarray):
+        host = np.ascontiguousarray(host)
+        self._ck(self._lib.gm2_upload(self._h, int(dev_ptr), _ptr(host), host.nbytes))
 
     # -- diagnostics ------------------------------------------------------------------------------
     def diag_fill(self, dev_ptr: int, nbytes: int, pattern: int = 0x41414141):

@@ -785,6 +785,30 @@ GM2_API int gm2_minimize_host(gm2_ctx* c, const int32_t* ids, const int64_t* off
     return gm2_emit_host(c, 0, S, host_out, cap, chunk_bytes);
 }
 
+GM2_API int gm2_device_alloc(gm2_ctx* c, void** out, int64_t bytes) {
+    if (!c || !out || bytes < 0) return GM2_ERR_INVALID;
+    *out = nullptr;
+    CU(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) { cuda_fail(c, e, "cudaMalloc"); return GM2_ERR_NOMEM; }
+    return GM2_OK;
+}
+GM2_API int gm2_device_free(gm2_ctx* c, void* p) {
+    if (!c) return GM2_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    if (p) { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaFree(p)); }
+    return GM2_OK;
+}
+GM2_API int gm2_upload(gm2_ctx* c, void* dev, const void* host, int64_t bytes) {
+    if (!c || bytes < 0 || (bytes > 0 && (!dev || !host))) return GM2_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    if (bytes > 0) {
+        CU(c, cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return GM2_OK;
+}
+
 GM2_API int gm2_host_alloc(void** out, int64_t bytes) {
     if (!out || bytes < 0) return GM2_ERR_INVALID;
     *out = nullptr;

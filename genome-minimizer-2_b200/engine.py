@@ -469,3 +469,69 @@ def run_single_file_from_probabilities(record, probs, col_names: Sequence[str], 
             tot_red += _pct(G, int(lengths[idx]))
             tot_len += int(lengths[idx])
     return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}
+
+
+def load_masks_npy(masks_npy_path: str) -> np.ndarray:
+    """The masks container `--mode convert-samples` reads (explore_data/binary_converter.py:38-46):
+    a 2-D float array [N, P], a 1-D object array of rows, or a single 1-D row."""
+    masks = np.load(masks_npy_path, allow_pickle=True)
+    if masks.ndim == 1:
+        if len(masks) and isinstance(masks[0], (list, np.ndarray)):
+            masks = np.array([np.asarray(row) for row in masks], dtype=object)
+        else:
+            masks = masks[None, :]
+    return masks
+
+
+def run_single_file_from_masks(record, masks_npy_path: str, col_names: Sequence[str], essential: Iterable[str],
+                               model_name: str, output_file: str, threshold: float = 0.5,
+                               engine: Optional[MinimizerEngine] = None) -> dict:
+    """`--mode convert-samples` + `--mode minimizer --single-file` from the masks FILE that `--mode sample`
+    writes (main.py:434): rows are thresholded exactly as the reference does (`np.asarray(row, float) >=
+    threshold`, binary_converter.py:49-55 — in float64, on the host), uploaded as 0/1 float32 and handed
+    to the dense keep-mask builder.  Same file, progress lines and return dict as the reference's chain."""
+    masks = load_masks_npy(masks_npy_path)
+    eng = engine or MinimizerEngine(record)
+    try:
+        space = ColumnSpace(eng.table, col_names, essential)
+        rows = []
+        for i, row in enumerate(masks):
+            r = np.asarray(row, dtype=float)
+            if r.size != space.V:
+                raise ValueError(f"Mask row {i} has length {r.size}, but dataset has {space.V} gene columns.")
+            rows.append(r >= threshold)
+        present = (np.stack(rows, axis=0) if rows else np.zeros((0, space.V), dtype=bool)).astype(np.float32)
+        dev = _DeviceMatrix(eng.ctx, present)
+        try:
+            return run_single_file_from_probabilities(record, dev, col_names, essential, model_name, output_file,
+                                                      threshold=0.5, engine=eng)
+        finally:
+            dev.free()
+    finally:
+        if engine is None:
+            eng.close()
+
+
+class _DeviceMatrix:
+    """A float32 [S, V] matrix uploaded to the engine's GPU with the CUDA runtime through ctypes, exposing
+    the torch-like surface `_device_matrix` reads (torch is plumbing for callers, not a dependency here)."""
+
+    def __init__(self, ctx: "_native.Context", host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=np.float32)
+        self.shape = host.shape
+        self.dtype = "float32"
+        self.is_cuda = True
+        self._ctx = ctx
+        self._buf = ctx.device_alloc(max(host.nbytes, 4))
+        ctx.upload(self._buf, host)
+
+    def data_ptr(self) -> int:
+        return self._buf
+
+    def stride(self):
+        return (self.shape[1], 1)
+
+    def free(self):
+        if self._buf:
+            self._ctx.device_free(self._buf)
+            self._buf = 0

@@ -170,6 +170,13 @@ int gm2_minimize_host(gm2_ctx* ctx, const int32_t* ids, const int64_t* off,
                       int64_t* lengths /* S */, int64_t* rec_off /* S+1 */,
                       uint8_t* host_out, int64_t cap, int64_t chunk_bytes);
 
+/* Device memory owned by the caller, for the *_dev entry points when the caller has no CUDA
+ * allocator of its own (a torch tensor's data_ptr() works just as well).  gm2_upload is a
+ * synchronous host-to-device copy on the context's stream. */
+int gm2_device_alloc(gm2_ctx* ctx, void** out, int64_t bytes);
+int gm2_device_free(gm2_ctx* ctx, void* p);
+int gm2_upload(gm2_ctx* ctx, void* dev, const void* host, int64_t bytes);
+
 /* Pinned host memory for output buffers. */
 int gm2_host_alloc(void** out, int64_t bytes);
 int gm2_host_free(void* p);

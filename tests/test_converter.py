@@ -89,3 +89,38 @@ def test_device_chain_matches_reference_file(name, tmp_path):
             engine.plan_from_probabilities(eng, space, wide)
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("container", ["2d-float64", "object-rows"])
+def test_masks_file_chain_matches_reference_file(name, container, tmp_path):
+    """From the masks FILE `--mode sample` writes (main.py:434) to the FASTA the reference's
+    convert-samples + minimizer chain produces."""
+    c = load_golden(name)
+    gb = tmp_path / "g.gb"
+    gb.write_text(c["genbank"])
+    rec = genbank.read_genbank(str(gb))
+    binary = (np.asarray(c["decoded"], dtype=np.float32) > 0.5).astype(float)       # utils/extras.py:199-201
+    masks = tmp_path / "binary_samples.npy"
+    if container == "2d-float64":
+        np.save(masks, binary)
+    else:
+        arr = np.empty(len(binary), dtype=object)
+        for i, row in enumerate(binary):
+            arr[i] = row.tolist()
+        np.save(masks, arr, allow_pickle=True)
+    out = tmp_path / "chain.fasta"
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ret = engine.run_single_file_from_masks(rec, str(masks), c["columns"], c["essential"], c["model_name"], str(out))
+    lines = out.read_bytes().decode().split("\n")
+    lines[2] = "# Generated on: <TS>"
+    assert "\n".join(lines) == c["single_file"]
+    assert buf.getvalue() == c["single_stdout"]
+    assert ret == c["single_return"]
+    # a row of the wrong length is refused with the reference's message
+    bad = tmp_path / "bad.npy"
+    np.save(bad, binary[:, :-1])
+    with pytest.raises(ValueError, match="gene columns"):
+        engine.run_single_file_from_masks(rec, str(bad), c["columns"], c["essential"], "m", str(tmp_path / "x.fasta"))
