@@ -534,3 +534,22 @@ def test_fuzz_kernel_configurations():
             ctx.plan(first)
             assert np.array_equal(ctx.lengths(), exp_len), (trial, cfg)
             assert np.array_equal(_gpu_image(ctx, S), exp_img), (trial, G, F, S, cfg)
+
+
+def test_integration_md_ctypes_stub_runs_as_written(tmp_path):
+    """The ctypes stub printed in INTEGRATION.md is executed verbatim against a golden case."""
+    from conftest import ROOT, load_golden
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text.split("ctypes stub", 1)[1].split("```python", 1)[1].split("```", 1)[0]
+    case = load_golden("kat_appB")
+    gb = tmp_path / "g.gb"
+    gb.write_text(case["genbank"])
+    cwd = os.getcwd()
+    os.chdir(ROOT)                                   # the stub loads the library by its in-tree relative path
+    try:
+        env = {"record": genbank.read_genbank(str(gb)), "all_lists": case["lists"]}
+        exec(compile(block, "INTEGRATION.md", "exec"), env)
+    finally:
+        os.chdir(cwd)
+    expected = "".join(case["single_file"].split("\n", 3)[3])      # records without the 3-line preamble
+    assert env["image"].tobytes().decode() == expected
