@@ -101,3 +101,51 @@ def run_single_file_sharded(record, all_lists: Sequence, model_name: str, output
             tot_red += _engine._pct(G, int(lengths[idx]))
             tot_len += int(lengths[idx])
     return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}
+
+
+def run_multi_file_sharded(record, all_lists: Sequence, model_name: str, output_dir,
+                           filename_template: str = "minimized_{model}_{idx:04d}.fasta",
+                           make_engine: Optional[Callable[[], object]] = None) -> dict:
+    """`process_multiple_genomes_multiple_files` (reference :499-560) over all ranks: every rank writes
+    the files of its own contiguous shard (global idx in the names and record ids); the lengths are
+    all-gathered so that every rank returns the reference's dict and rank 0 prints its lines."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = len(all_lists)
+    G = len(record.seq)
+    lo, hi = _engine.shard_range(n, rank, world)
+    if rank == 0:
+        os.makedirs(output_dir, exist_ok=True)
+    dist.barrier()
+    eng = make_engine() if make_engine is not None else _engine.MinimizerEngine(record)
+    try:
+        local_len = np.asarray(eng.plan_lists(all_lists[lo:hi], first_idx=lo), dtype=np.int64)
+        sizes = np.asarray([header_len(lo + i) for i in range(hi - lo)], dtype=np.int64) + local_len + 1
+        rel = np.zeros(hi - lo + 1, dtype=np.int64)
+        rel[1:] = np.cumsum(sizes)
+
+        def sink(sa: int, sb: int, view: np.ndarray) -> None:
+            base = int(rel[sa])
+            for s in range(sa, sb):
+                fname = filename_template.format(model=model_name, idx=lo + s)
+                with open(os.path.join(output_dir, fname), "wb") as fh:
+                    fh.write(view[int(rel[s]) - base:int(rel[s + 1]) - base])
+
+        eng.drain(sink)
+        lengths = np.concatenate(all_gather_lengths(local_len)) if n else np.zeros(0, dtype=np.int64)
+        dist.barrier()
+    finally:
+        if make_engine is None:
+            eng.close()
+    if rank == 0:
+        print(f"Writing {n} individual FASTA files to: {output_dir}")
+        for idx in range(n):
+            print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
+            if _engine._sampled(idx):
+                L = int(lengths[idx])
+                fname = filename_template.format(model=model_name, idx=idx)
+                print(f"  → saved {fname} | {L:,} bp ({_engine._pct(G, L):.1f}% reduction)")
+    tot_red, tot_len = 0.0, 0
+    for idx in range(n):
+        tot_red += _engine._pct(G, int(lengths[idx]))
+        tot_len += int(lengths[idx])
+    return {"genome_count": n, "average_reduction_pct": tot_red / n, "average_length_bp": tot_len / n}

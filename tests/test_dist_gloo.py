@@ -34,6 +34,28 @@ class OracleEngine:
             sink(i, i + 1, np.frombuffer(img, dtype=np.uint8))
 
 
+def _worker_multi(rank, world, port, case_name, out_dir, ret_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import tempfile
+        from oracle import genbank_reader
+        from genome_minimizer_2_b200 import dist as gdist
+        case = load_golden(case_name)
+        with tempfile.NamedTemporaryFile("w", suffix=".gb", delete=False) as fh:
+            fh.write(case["genbank"])
+        rec = genbank_reader.read_genbank(fh.name)
+        os.unlink(fh.name)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ret = gdist.run_multi_file_sharded(rec, case["lists"], case["model_name"], out_dir,
+                                               make_engine=lambda: OracleEngine(rec))
+        with open(f"{ret_path}.{rank}", "w") as fh:
+            json.dump({"ret": ret, "stdout": buf.getvalue()}, fh)
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, case_name, out_path, ret_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -83,3 +105,20 @@ def test_two_ranks_hundred_and_one_samples(tmp_path):
 
 def test_three_ranks_uneven_shards(tmp_path):
     _run("rand_small_1", tmp_path, world=3)    # 17 samples over 3 ranks
+
+
+def test_two_ranks_multi_file_mode(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "multi")
+    retp = str(tmp_path / "ret")
+    mp.spawn(_worker_multi, args=(2, port, "hundred_and_one", out, retp), nprocs=2, join=True)
+    case = load_golden("hundred_and_one")
+    files = {fn: open(os.path.join(out, fn), "rb").read().decode() for fn in sorted(os.listdir(out))}
+    assert files == case["multi_files"]
+    r = [json.load(open(f"{retp}.{k}")) for k in range(2)]
+    assert all(x["ret"] == case["multi_return"] for x in r)
+    assert r[0]["stdout"].replace(out, "<OUTDIR>") == case["multi_stdout"] and r[1]["stdout"] == ""
