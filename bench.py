@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--store-policy", type=int, default=-1)
     ap.add_argument("--packing", type=int, default=0)
     ap.add_argument("--emit-order", type=int, default=-1)
+    ap.add_argument("--flat-run-bytes", type=int, default=-1, help="GM2_CFG_FLAT_RUN_BYTES (0 never, 1048576 always)")
     ap.add_argument("--emit-debug", type=int, default=0, help="timing experiments only (wrong output)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -346,6 +347,8 @@ def main():
         ctx.configure(_native.CFG_STORE_POLICY, args.store_policy)
     if args.emit_order >= 0:
         ctx.configure(_native.CFG_ORDER, args.emit_order)
+    if args.flat_run_bytes >= 0:
+        ctx.configure(_native.CFG_FLAT_RUN_BYTES, args.flat_run_bytes)
     if args.emit_debug:
         ctx.configure(_native.CFG_DEBUG, args.emit_debug)
         args.verify = 0

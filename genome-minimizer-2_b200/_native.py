@@ -18,6 +18,7 @@ ABI_VERSION = 1
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM = -1, -2, -3, -4, -5
 CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY, CFG_RUN_TABLE, CFG_DEBUG, CFG_ORDER = 1, 2, 3, 4, 5, 6, 7, 8
+CFG_FLAT_RUN_BYTES = 9
 Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS = 1, 2, 3, 4, 5, 6, 7
 
 _c = ctypes

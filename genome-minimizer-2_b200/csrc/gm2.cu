@@ -66,6 +66,7 @@ struct gm2_ctx {
     int rt_cap = 64;
     int debug = 0;
     int order = 1;
+    int flat_run_bytes = 640;      // see emit_runs_flat; measured crossover in profiles/r01_emit_experiments.md
     HeaderPrefix prefix;
 
     // reference
@@ -252,6 +253,9 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     case GM2_CFG_ORDER:
         if (value != 0 && value != 1) return fail(c, GM2_ERR_INVALID, "order must be 0 (tile-major) or 1 (sample-major)");
         c->order = (int)value; return GM2_OK;
+    case GM2_CFG_FLAT_RUN_BYTES:
+        if (value < 0 || value > (1 << 20)) return fail(c, GM2_ERR_INVALID, "flat run bytes must be in 0..1048576");
+        c->flat_run_bytes = (int)value; return GM2_OK;
     case GM2_CFG_DEBUG:
         c->debug = (int)value; return GM2_OK;
     case GM2_CFG_RUN_TABLE:
@@ -701,7 +705,7 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW; p.batch = (int)batch; p.nbatch = (int)nbatch;
     p.rt_cap = c->rt_cap;
     p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
-    p.prefix = c->prefix; p.debug = c->debug; p.order = c->order;
+    p.prefix = c->prefix; p.debug = c->debug; p.order = c->order; p.flat_run_bytes = c->flat_run_bytes;
     const size_t sm = 32 + (size_t)p.tile_smem_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 24;
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
     // register budget follows the shared-memory footprint: small tiles -> 4+ CTAs/SM (64 regs),

@@ -39,6 +39,7 @@ struct EmitParams {
     int rt_cap;            // run-table entries per warp (shared memory)
     int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
     int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
+    int flat_run_bytes;    // batches whose mean run length is below this take emit_runs_flat (0: never)
     int debug;             // timing experiments only (wrong output; needs -DGM2_EMIT_DEBUG): 1 no boundary
                            // sectors, 2 no interior stores, 4 interior stores without shared loads
     HeaderPrefix prefix;
@@ -256,6 +257,100 @@ __device__ __forceinline__ void emit_runs(uint32_t tile_a, uint32_t rt_a, uint32
     __syncwarp();
 }
 
+
+// Flat form of emit_runs for batches of SHORT runs (mean run length below EmitParams::flat_run_bytes).
+// The run-by-run stream above pays ~50 warp instructions per run besides the copy, which bounds the
+// kernel once runs are a few hundred bytes (low retention: every intergenic gap between two deleted
+// genes is a run of its own).  Here the unit of work is a destination-aligned 16-byte vector and the
+// lanes do not share a run:
+//   phase B  lane <-> run boundary: the vector a boundary falls into is assembled byte by byte in
+//            registers (private cursor into table A) and leaves as one 128-bit store;
+//   phase I  lane <-> vector, stride 32: each lane walks table A with its own cursor; a vector that
+//            lies inside one run is two aligned 128-bit shared loads, a per-lane word select + byte
+//            funnel shift, one 128-bit store.  Lanes 2j, 2j+1 still fill one sector per instruction;
+//   phase E  the partial first / last vector of the batch (shared with the neighbouring tile's warp),
+//            lane <-> byte as in the stream form.
+// Both halves of a sector are written within the same (sample, tile) visit, i.e. well inside the time
+// a line stays in L2, so no partial sector reaches DRAM.  Table B is not built.
+template <int POLICY>
+__device__ __forceinline__ void emit_runs_flat(uint32_t tile_a, uint32_t rt_a, int nr,
+                                               uint8_t* __restrict__ base32, int lane)
+{
+    const int q_first = rt_load(rt_a).x, q_last = rt_load(rt_a + 8 * nr).x;
+    // ---- phase B: vectors holding a run boundary (whole vectors only; the batch's edges are phase E)
+    for (int r0 = 1; r0 < nr; r0 += 32) {
+        const int r = r0 + lane;
+        if (r < nr) {
+            const int qr = rt_load(rt_a + 8 * r).x;
+            const int p0 = qr & ~15;
+            bool own = (qr & 15) && p0 >= q_first && p0 + 16 <= q_last;
+            uint32_t ra = rt_a + 8 * (r - 1);
+            int2 e = rt_load(ra);
+            if ((e.x & ~15) == p0 && (e.x & 15)) own = false;                // an earlier boundary owns this vector
+            if (own) {
+                int qn = qr;
+                uint32_t ab = tile_a + (uint32_t)(e.y - e.x + p0);              // shared address of byte p0 if it were in run rr
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    while (p0 + j >= qn) {
+                        ra += 8; e = rt_load(ra); qn = rt_load(ra + 8).x;
+                        ab = tile_a + (uint32_t)(e.y - e.x + p0);
+                    }
+                    w[j >> 2] |= lds8(ab + j) << (8 * (j & 3));
+                }
+                st128<POLICY>(base32 + p0, make_uint4(w[0], w[1], w[2], w[3]));
+            }
+        }
+    }
+    // ---- phase I: vectors inside one run
+    {
+        const int v_hi = q_last >> 4;
+        uint32_t ra = rt_a;
+        int2 e = rt_load(ra);
+        int qn = rt_load(ra + 8).x;
+#pragma unroll 1
+        for (int v = ((q_first + 15) >> 4) + lane; v < v_hi; v += 32) {
+            const int pos = v << 4;
+            while (pos >= qn) { ra += 8; e = rt_load(ra); qn = rt_load(ra + 8).x; }
+            if (pos + 16 <= qn) {
+                const uint32_t a = tile_a + (uint32_t)(e.y + (pos - e.x));
+                const uint32_t qa = a & ~15u;
+                const int sh = (int)(a & 3u) * 8;
+                const uint4 lo = lds128(qa), hi = lds128(qa + 16);
+                uint32_t w0 = lo.x, w1 = lo.y, w2 = lo.z, w3 = lo.w, w4 = hi.x, w5 = hi.y, w6 = hi.z;
+                if (a & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = hi.w; }
+                if (a & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+                uint4 o;
+                o.x = __funnelshift_r(w0, w1, sh);
+                o.y = __funnelshift_r(w1, w2, sh);
+                o.z = __funnelshift_r(w2, w3, sh);
+                o.w = __funnelshift_r(w3, w4, sh);
+                st128<POLICY>(base32 + pos, o);
+            }
+        }
+    }
+    // ---- phase E: partial vectors at the two ends of the batch
+    {
+        const int vf = q_first >> 4, vl = q_last >> 4;
+        int pos = -1;
+        if (lane < 16) { if (q_first & 15) pos = (vf << 4) + lane; }
+        else if ((q_last & 15) && !((q_first & 15) && vl == vf)) pos = (vl << 4) + (lane - 16);
+        if (pos >= q_first && pos < q_last) {
+            int2 e;
+            if (lane < 16) {
+                uint32_t ra = rt_a; e = rt_load(ra); int qn = rt_load(ra + 8).x;
+                while (pos >= qn) { ra += 8; e = rt_load(ra); qn = rt_load(ra + 8).x; }
+            } else {
+                uint32_t ra = rt_a + 8 * (nr - 1); e = rt_load(ra);
+                while (pos < e.x) { ra -= 8; e = rt_load(ra); }
+            }
+            st8<POLICY>(base32 + pos, lds8(tile_a + (uint32_t)(e.y + (pos - e.x))));
+        }
+    }
+    __syncwarp();
+}
+
 #define EMIT_FRONT_PAD 32
 #define EMIT_BACK_PAD  64
 
@@ -363,7 +458,11 @@ k_emit(const EmitParams p)
                 if (done || nr + 17 > p.rt_cap) {               // tile finished, or table full: emit what we have
                     if (nr > 0) {
                         if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
-                        emit_runs<POLICY, PACK>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
+                        __syncwarp();
+                        if (PACK == 1 && q - rt_load(rt_a).x < nr * p.flat_run_bytes)
+                            emit_runs_flat<POLICY>(tile_a, rt_a, nr, base32, lane);
+                        else
+                            emit_runs<POLICY, PACK>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);
                         nr = 0; carry = 0u;
                     }
                     if (done) break;

@@ -53,6 +53,9 @@ extern "C" {
 #define GM2_CFG_STORE_POLICY  5  /* 0 plain stores, 1 streaming st.global.cs (default)       */
 #define GM2_CFG_RUN_TABLE     6  /* kept-run table entries per warp in shared memory (32..1024) */
 #define GM2_CFG_ORDER         8  /* emit CTA order: 0 tile-major, 1 sample-major (default)   */
+#define GM2_CFG_FLAT_RUN_BYTES 9 /* (sample, tile) batches whose mean kept-run length is below this many bytes use the
+                                    vector-per-lane emit path instead of the run-by-run stream; 0 = never, 1048576 = always
+                                    (default 640; byte packing only) */
 #define GM2_CFG_DEBUG         7  /* timing knock-outs (WRONG output); only effective in -DGM2_EMIT_DEBUG builds */
 
 /* gm2_query keys */

@@ -44,6 +44,7 @@ def test_header_constants_match_binding():
                  ("GM2_ERR_NOMEM", _native.ERR_NOMEM), ("GM2_CFG_TILE_BYTES", _native.CFG_TILE_BYTES),
                  ("GM2_CFG_EMIT_WARPS", _native.CFG_EMIT_WARPS), ("GM2_CFG_EMIT_BATCH", _native.CFG_EMIT_BATCH),
                  ("GM2_CFG_PACKING", _native.CFG_PACKING), ("GM2_CFG_STORE_POLICY", _native.CFG_STORE_POLICY),
+                 ("GM2_CFG_FLAT_RUN_BYTES", _native.CFG_FLAT_RUN_BYTES), ("GM2_CFG_ORDER", _native.CFG_ORDER),
                  ("GM2_Q_LAUNCHES", _native.Q_LAUNCHES), ("GM2_Q_KEEP_WORDS", _native.Q_KEEP_WORDS)):
         assert int(consts[k]) == v, k
 

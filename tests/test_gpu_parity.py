@@ -303,10 +303,11 @@ def test_dense_tiny_genes_exercise_table_flush_and_global_slot_path():
     S = 21
     rows = synth.pack_keep_rows(rng.random((S, F)) < np.linspace(0.05, 0.95, S)[:, None])
     exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows)
-    for rt_cap, warps in ((32, 8), (64, 4), (1024, 2)):
+    for rt_cap, warps, flat in ((32, 8, 0), (64, 4, 640), (1024, 2, 1 << 20), (32, 8, 1 << 20), (1024, 1, 0)):
         with _native.Context(0) as ctx:
             ctx.configure(_native.CFG_RUN_TABLE, rt_cap)
             ctx.configure(_native.CFG_EMIT_WARPS, warps)
+            ctx.configure(_native.CFG_FLAT_RUN_BYTES, flat)
             ctx.set_reference(seq, starts, ends)
             assert ctx.query(_native.Q_NUM_SLOTS) > 4096
             ctx.load_keep_host(rows)
@@ -525,6 +526,7 @@ def test_fuzz_kernel_configurations():
             _native.CFG_STORE_POLICY: int(rng.choice([0, 1])),
             _native.CFG_ORDER: int(rng.choice([0, 1])),
             _native.CFG_EMIT_BATCH: int(rng.choice([0, 1, 3, 16])),
+            _native.CFG_FLAT_RUN_BYTES: int(rng.choice([0, 64, 640, 1 << 20])),
         }
         with _native.Context(0) as ctx:
             for k, v in cfg.items():
