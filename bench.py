@@ -307,6 +307,32 @@ def dropin_c1(g, table, args):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def lists_tokenize_bench(g, table, n_lists=1000):
+    """SURVEY.md §8 f2 beside the GPU numbers: the `.npy` gene-lists file -> id CSR on the host, natively
+    (gm2_tokenize_pickle) vs the reference's loading path restated (np.load(...).tolist() + per-name
+    lookup).  Wall clock on one host core; results compared."""
+    import shutil
+    from genome_minimizer_2_b200 import engine, synth
+    d = tempfile.mkdtemp(prefix="gm2_tok_")
+    try:
+        npy = os.path.join(d, "lists.npy")
+        lists = synth.make_gene_lists(g, n_lists, 0.5, seed=2, extra_names=2000)
+        synth.save_gene_lists(npy, lists)
+        del lists
+        t0 = time.perf_counter()
+        tok = engine.load_gene_lists(npy, table)
+        t_native = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ids, off = table.tokenize(np.load(npy, allow_pickle=True).tolist())
+        t_python = time.perf_counter() - t0
+        if not (isinstance(tok, engine.TokenizedLists) and np.array_equal(tok.ids, ids) and np.array_equal(tok.off, off)):
+            raise SystemExit("bench.py: native tokeniser disagrees with the NumPy/Python path")
+        return {"workload": f"{n_lists} gene-name lists (.npy, {os.path.getsize(npy) / 1e6:.1f} MB, {ids.size} matching names)",
+                "native_seconds": t_native, "numpy_python_seconds": t_python, "cores": 1}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 # ----------------------------------------------------------------------------------------------
 # ours
 # ----------------------------------------------------------------------------------------------
@@ -587,6 +613,7 @@ def main():
     dropin = None
     if world == 1 and not args.no_dropin:
         dropin = dropin_c1(g, table, args)
+        dropin["lists_tokenize"] = lists_tokenize_bench(g, table)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

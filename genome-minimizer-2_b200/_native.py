@@ -16,7 +16,7 @@ from . import build as _build
 # ---- constants mirrored from include/gm2.h -------------------------------------------------
 ABI_VERSION = 1
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM = -1, -2, -3, -4, -5
+ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY, CFG_RUN_TABLE, CFG_DEBUG, CFG_ORDER = 1, 2, 3, 4, 5, 6, 7, 8
 CFG_FLAT_RUN_BYTES = 9
 Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS = 1, 2, 3, 4, 5, 6, 7
@@ -64,6 +64,7 @@ SIGNATURES = {
     "gm2_diag_fill": (_c.c_int, [_P, _P, _I64, _c.c_uint32]),
     "gm2_diag_fill_streams": (_c.c_int, [_P, _P, _I64, _I64, _c.c_int32, _I64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
     "gm2_diag_range_hashes": (_c.c_int, [_P, _P, _I64, _P, _I64, _P]),
+    "gm2_tokenize_pickle": (_c.c_int, [_P, _I64, _I64, _I64, _P, _P, _c.c_int32, _P, _I64, _P, _P]),
 }
 
 _lib = None
@@ -110,6 +111,48 @@ def _ptr(a) -> Optional[int]:
     if isinstance(a, (int, np.integer)):
         return int(a)
     return a.ctypes.data
+
+
+def tokenize_npy(path: str, names) -> Optional[tuple]:
+    """Gene-name lists file -> (ids int32, off int64[S+1], counts int64[S]) through gm2_tokenize_pickle,
+    or None when the file is not in the subset the native tokeniser handles (the caller then uses
+    `np.load(path, allow_pickle=True).tolist()`, minimizer_2.py:456).  `names[v]` is the vocabulary
+    (id v).  Host only; raises what `np.load` would raise for a missing / unreadable file."""
+    from numpy.lib import format as npf
+    with open(path, "rb") as fh:
+        try:
+            version = npf.read_magic(fh)
+            if version == (1, 0):
+                shape, _fortran, dtype = npf.read_array_header_1_0(fh)
+            elif version == (2, 0):
+                shape, _fortran, dtype = npf.read_array_header_2_0(fh)
+            else:
+                return None
+        except ValueError:
+            return None                                   # not a .npy file (np.load has more formats)
+        if not dtype.hasobject or dtype != np.dtype(object) or len(shape) not in (1, 2):
+            return None
+        body = np.fromfile(fh, dtype=np.uint8)
+    S = int(shape[0])
+    L = int(shape[1]) if len(shape) == 2 else 0
+    if body.size == 0 or (len(shape) == 2 and L == 0):
+        return None
+    enc = [str(n).encode("utf-8", "surrogatepass") for n in names]
+    blob = np.frombuffer(b"".join(enc), dtype=np.uint8) if enc else np.zeros(0, dtype=np.uint8)
+    name_off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        name_off[1:] = np.cumsum([len(e) for e in enc])
+    cap = body.size // 2 + 16
+    ids = np.empty(cap, dtype=np.int32)
+    off = np.empty(S + 1, dtype=np.int64)
+    counts = np.empty(S, dtype=np.int64)
+    if blob.size == 0:
+        blob = np.zeros(1, dtype=np.uint8)
+    rc = load().gm2_tokenize_pickle(_ptr(body), body.size, S, L, _ptr(blob), _ptr(name_off), len(enc),
+                                    _ptr(ids), cap, _ptr(off), _ptr(counts))
+    if rc != OK:
+        return None               # unsupported or corrupt: NumPy's loader decides (and raises its own errors)
+    return ids[:int(off[-1])].copy(), off, counts
 
 
 class PinnedBuffer:

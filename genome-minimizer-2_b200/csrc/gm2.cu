@@ -27,6 +27,7 @@
 #include <new>
 
 #include "gm2.h"
+#include "host_tokenize.hpp"
 
 #define GM2_API extern "C" __attribute__((visibility("default")))
 
@@ -933,3 +934,54 @@ GM2_API int gm2_diag_range_hashes(gm2_ctx* c, const uint8_t* dev, int64_t dev_by
     return rc;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// host-only: gene-name lists container -> id CSR (see host_tokenize.hpp)
+// ------------------------------------------------------------------------------------------
+GM2_API int gm2_tokenize_pickle(const uint8_t* body, int64_t nbytes, int64_t S, int64_t L,
+                                const char* names, const int64_t* name_off, int32_t V,
+                                int32_t* ids_out, int64_t ids_cap, int64_t* off_out, int64_t* count_out) {
+    if (!body || nbytes <= 0 || S < 0 || L < 0 || V < 0 || (V > 0 && (!names || !name_off)) || !off_out || !count_out ||
+        (ids_cap > 0 && !ids_out))
+        return fail(nullptr, GM2_ERR_INVALID, "gm2_tokenize_pickle: bad argument");
+    try {
+        gm2tok::Machine m;
+        m.p = body; m.end = body + nbytes;
+        m.vocab.reserve((size_t)V * 2);
+        for (int32_t v = 0; v < V; ++v)
+            m.vocab.emplace(std::string_view(names + name_off[v], (size_t)(name_off[v + 1] - name_off[v])), v);
+        const int rc = m.run();
+        if (rc == 1) return fail(nullptr, GM2_ERR_UNSUPPORTED, "gm2_tokenize_pickle: pickle opcode outside the supported subset");
+        if (rc != 0) return fail(nullptr, GM2_ERR_INVALID, "gm2_tokenize_pickle: corrupt pickle stream");
+        // the outermost object is built last: its state is (version, shape, dtype, fortran, [elements])
+        if (m.last_state < 0 || m.seqs[m.last_state].empty() || !gm2tok::is_seq(m.seqs[m.last_state].back()))
+            return fail(nullptr, GM2_ERR_UNSUPPORTED, "gm2_tokenize_pickle: not a pickled object array");
+        const std::vector<gm2tok::Item>& flat = m.seqs[gm2tok::seq_index(m.seqs[m.last_state].back())];
+        const int64_t want = L > 0 ? S * L : S;
+        if ((int64_t)flat.size() != want) return fail(nullptr, GM2_ERR_INVALID, "gm2_tokenize_pickle: element count does not match the shape");
+        int64_t n = 0;
+        off_out[0] = 0;
+        for (int64_t i = 0; i < S; ++i) {
+            const int32_t* it; int64_t cnt;
+            if (L > 0) { it = flat.data() + i * L; cnt = L; }
+            else {
+                if (!gm2tok::is_seq(flat[i])) return fail(nullptr, GM2_ERR_UNSUPPORTED, "gm2_tokenize_pickle: an element is not a list");
+                const std::vector<gm2tok::Item>& lst = m.seqs[gm2tok::seq_index(flat[i])];
+                it = lst.data(); cnt = (int64_t)lst.size();
+            }
+            for (int64_t k = 0; k < cnt; ++k) {
+                const int32_t t = it[k];
+                if (t < gm2tok::IT_UNKNOWN_STR) return fail(nullptr, GM2_ERR_UNSUPPORTED, "gm2_tokenize_pickle: a list item is not a str");
+                if (t >= 0) {
+                    if (n >= ids_cap) return fail(nullptr, GM2_ERR_CAPACITY, "gm2_tokenize_pickle: ids_out too small");
+                    ids_out[n++] = t;
+                }
+            }
+            count_out[i] = cnt;
+            off_out[i + 1] = n;
+        }
+        return GM2_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(nullptr, GM2_ERR_NOMEM, "gm2_tokenize_pickle: out of host memory");
+    }
+}

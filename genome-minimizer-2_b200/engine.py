@@ -94,6 +94,13 @@ class GeneTable:
         ids = np.fromiter((i for r in rows for i in r), dtype=np.int32, count=int(off[-1]))
         return ids, off
 
+    def vocabulary(self) -> List[str]:
+        """Distinct gene names, position = id (the id space of `tokenize` and gm2_set_name_map)."""
+        out = [""] * len(self.name_to_id)
+        for nm, i in self.name_to_id.items():
+            out[i] = nm
+        return out
+
     def keep_rows_from_bool(self, keep: np.ndarray) -> np.ndarray:
         """Boolean [S, F] -> packed little-endian uint32 rows [S, ceil(F/32)]."""
         keep = np.atleast_2d(np.asarray(keep, dtype=bool))
@@ -102,6 +109,52 @@ class GeneTable:
         padded = np.zeros((S, fw * 32), dtype=np.uint8)
         padded[:, :F] = keep
         return np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(S, fw)
+
+
+class _Sized:
+    """Stands in for one gene list where only its len() is still needed (the progress lines)."""
+    __slots__ = ("_n",)
+
+    def __init__(self, n: int):
+        self._n = n
+
+    def __len__(self) -> int:
+        return self._n
+
+
+class TokenizedLists:
+    """The gene-name lists of a file as an id CSR: what `GeneTable.tokenize` makes of
+    `np.load(genes_path, allow_pickle=True).tolist()` (minimizer_2.py:456, :518), produced straight from
+    the file's pickle stream by gm2_tokenize_pickle.  Ids are those of a GeneTable built from the same
+    record.  Behaves like the list of lists where the entry functions use it: len(), [a:b], len(x[i])."""
+
+    def __init__(self, ids: np.ndarray, off: np.ndarray, counts: np.ndarray):
+        self.ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self.off = np.ascontiguousarray(off, dtype=np.int64)
+        self.counts = np.ascontiguousarray(counts, dtype=np.int64)
+
+    def __len__(self) -> int:
+        return int(self.counts.size)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            lo, hi, step = i.indices(len(self))
+            if step != 1:
+                raise ValueError("TokenizedLists supports contiguous slices only")
+            hi = max(hi, lo)
+            a, b = int(self.off[lo]), int(self.off[hi])
+            return TokenizedLists(self.ids[a:b], self.off[lo:hi + 1] - a, self.counts[lo:hi])
+        return _Sized(int(self.counts[i]))
+
+
+def load_gene_lists(genes_path: str, table: GeneTable):
+    """`np.load(genes_path, allow_pickle=True).tolist()` (minimizer_2.py:456, :518), tokenised natively
+    when the file is an object array of lists of str; any other content goes through NumPy itself and
+    comes back as the plain Python object (same errors, same `in` semantics downstream)."""
+    tok = _native.tokenize_npy(os.fspath(genes_path), table.vocabulary())
+    if tok is not None:
+        return TokenizedLists(*tok)
+    return np.load(genes_path, allow_pickle=True).tolist()
 
 
 def default_device() -> int:
@@ -143,6 +196,8 @@ class MinimizerEngine:
 
     # -- planning ---------------------------------------------------------------------------
     def plan_lists(self, all_lists: Iterable, first_idx: int = 0) -> np.ndarray:
+        if isinstance(all_lists, TokenizedLists):
+            return self.plan_ids(all_lists.ids, all_lists.off, first_idx)
         ids, off = self.table.tokenize(all_lists)
         return self.plan_ids(ids, off, first_idx)
 

@@ -141,7 +141,7 @@ def process_multiple_genomes_single_file(genome_path: str, genes_path: str, mode
         output_file = os.path.join(_default_dir(), f"minimized_genomes_{model_name}.fasta")
     os.makedirs(os.path.dirname(output_file), exist_ok=True)
     record = read_genbank(os.fspath(genome_path))                      # reference :455
-    all_lists = np.load(genes_path, allow_pickle=True).tolist()        # reference :456
+    all_lists = _engine.load_gene_lists(genes_path, _engine.GeneTable.from_record(record))   # reference :456
     return _engine.run_single_file(record, all_lists, model_name, output_file)
 
 
@@ -153,5 +153,5 @@ def process_multiple_genomes_multiple_files(genome_path: str, genes_path: str, m
         output_dir = _default_dir()
     os.makedirs(output_dir, exist_ok=True)
     record = read_genbank(os.fspath(genome_path))                      # reference :515
-    all_lists = np.load(genes_path, allow_pickle=True).tolist()        # reference :518
+    all_lists = _engine.load_gene_lists(genes_path, _engine.GeneTable.from_record(record))   # reference :518
     return _engine.run_multi_file(record, all_lists, model_name, output_dir, filename_template)

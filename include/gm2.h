@@ -44,6 +44,7 @@ extern "C" {
 #define GM2_ERR_STATE    -3   /* call made in the wrong order                  */
 #define GM2_ERR_CAPACITY -4   /* caller's output buffer is too small           */
 #define GM2_ERR_NOMEM    -5   /* host or device allocation failed              */
+#define GM2_ERR_UNSUPPORTED -6 /* input outside the subset this entry point handles (caller has a slower general path) */
 
 /* gm2_configure keys */
 #define GM2_CFG_TILE_BYTES    1  /* reference bases staged per CTA (multiple of 4096; before set_reference) */
@@ -201,6 +202,21 @@ int gm2_diag_fill_streams(gm2_ctx* ctx, uint8_t* dev, int64_t nrec, int64_t stri
  * without copying 26 GB to the host.  `off` and `out` are host arrays. */
 int gm2_diag_range_hashes(gm2_ctx* ctx, const uint8_t* dev, int64_t dev_bytes,
                           const int64_t* off /* n+1 */, int64_t n, uint64_t* out /* n */);
+
+/* Host only (no context, no GPU).  Gene-name lists container -> id CSR, replacing
+ * `np.load(genes_path, allow_pickle=True).tolist()` (minimizer_2.py:456, :518) plus the per-name
+ * `name in needed_genes` test of :62 for the file `np.save` wrote at binary_converter.py:71 / :117.
+ * `body` is the pickle that follows the .npy header (dtype object); the array has S elements
+ * (1-D: each a list/tuple of str, L = 0) or S x L elements (2-D: each a str, L > 0).
+ * `names` + `name_off[V+1]` is the vocabulary (UTF-8, id = position; gm2_set_name_map's ids).
+ * Out: off_out[S+1], ids_out[off_out[S]] = vocabulary ids of the names that are in the
+ * vocabulary, in list order with duplicates; count_out[S] = len() of each list (all items).
+ * Returns GM2_ERR_UNSUPPORTED for anything but lists of plain str (the caller then uses NumPy's
+ * loader), GM2_ERR_INVALID for a corrupt stream or a shape mismatch, GM2_ERR_CAPACITY when
+ * ids_cap is too small (nbytes / 2 always suffices).  Message: gm2_last_error(NULL). */
+int gm2_tokenize_pickle(const uint8_t* body, int64_t nbytes, int64_t S, int64_t L,
+                        const char* names, const int64_t* name_off, int32_t V,
+                        int32_t* ids_out, int64_t ids_cap, int64_t* off_out, int64_t* count_out);
 
 #ifdef __cplusplus
 }

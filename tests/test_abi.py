@@ -41,7 +41,7 @@ def test_header_constants_match_binding():
     assert int(consts["GM2_ABI_VERSION"]) == _native.ABI_VERSION
     for k, v in (("GM2_ERR_INVALID", _native.ERR_INVALID), ("GM2_ERR_CUDA", _native.ERR_CUDA),
                  ("GM2_ERR_STATE", _native.ERR_STATE), ("GM2_ERR_CAPACITY", _native.ERR_CAPACITY),
-                 ("GM2_ERR_NOMEM", _native.ERR_NOMEM), ("GM2_CFG_TILE_BYTES", _native.CFG_TILE_BYTES),
+                 ("GM2_ERR_NOMEM", _native.ERR_NOMEM), ("GM2_ERR_UNSUPPORTED", _native.ERR_UNSUPPORTED), ("GM2_CFG_TILE_BYTES", _native.CFG_TILE_BYTES),
                  ("GM2_CFG_EMIT_WARPS", _native.CFG_EMIT_WARPS), ("GM2_CFG_EMIT_BATCH", _native.CFG_EMIT_BATCH),
                  ("GM2_CFG_PACKING", _native.CFG_PACKING), ("GM2_CFG_STORE_POLICY", _native.CFG_STORE_POLICY),
                  ("GM2_CFG_FLAT_RUN_BYTES", _native.CFG_FLAT_RUN_BYTES), ("GM2_CFG_ORDER", _native.CFG_ORDER),
