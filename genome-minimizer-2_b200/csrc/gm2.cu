@@ -128,6 +128,12 @@ static int cuda_fail(gm2_ctx* c, cudaError_t e, const char* what) {
 }
 #define CU(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail((c), e__, #call); } while (0)
 
+// A C++ exception must not cross the C ABI: entry points that allocate host memory are function-try-blocks.
+#define GM2_CATCH(c, who) \
+    catch (const std::bad_alloc&) { return fail((c), GM2_ERR_NOMEM, who ": out of host memory"); } \
+    catch (const std::exception& e__) { return fail((c), GM2_ERR_INVALID, std::string(who ": ") + e__.what()); }
+
+
 template <typename T>
 static int dev_reserve(gm2_ctx* c, T** p, int64_t* cap, int64_t need) {
     if (need <= *cap && *p) return GM2_OK;
@@ -305,7 +311,7 @@ GM2_API int gm2_set_header_prefix(gm2_ctx* c, const char* prefix) {
 
 GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
                               const int64_t* gs, const int64_t* ge, int32_t F)
-{
+try {
     if (!c) return GM2_ERR_INVALID;
     if (G < 0 || F < 0 || (G > 0 && !seq) || (F > 0 && (!gs || !ge)))
         return fail(c, GM2_ERR_INVALID, "gm2_set_reference: bad arguments");
@@ -420,9 +426,9 @@ GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
     }
     c->have_ref = true; c->planned = false; c->host_plan = false; c->mode = 0; c->S = 0;
     return GM2_OK;
-}
+} GM2_CATCH(c, "gm2_set_reference")
 
-GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx, int32_t V) {
+GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx, int32_t V) try {
     if (!c) return GM2_ERR_INVALID;
     if (!c->have_ref) return fail(c, GM2_ERR_STATE, "gm2_set_name_map: call gm2_set_reference first");
     if (V < 0 || !off) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: bad arguments");
@@ -457,7 +463,7 @@ GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx,
     if (c->d_forced_ids) { cudaFree(c->d_forced_ids); c->d_forced_ids = nullptr; }
     if (c->d_force_keep) { cudaFree(c->d_force_keep); c->d_force_keep = nullptr; }
     return GM2_OK;
-}
+} GM2_CATCH(c, "gm2_set_name_map")
 
 static int begin_samples(gm2_ctx* c, int64_t S, const char* who) {
     if (!c) return GM2_ERR_INVALID;
@@ -495,7 +501,7 @@ GM2_API int gm2_load_ids_dev(gm2_ctx* c, const int32_t* ids, const int64_t* off,
     return GM2_OK;
 }
 
-GM2_API int gm2_set_forced(gm2_ctx* c, const uint32_t* force_keep, const uint32_t* forced_ids) {
+GM2_API int gm2_set_forced(gm2_ctx* c, const uint32_t* force_keep, const uint32_t* forced_ids) try {
     if (!c) return GM2_ERR_INVALID;
     if (!c->d_first_gene) return fail(c, GM2_ERR_STATE, "gm2_set_forced: call gm2_set_name_map first");
     CU(c, cudaSetDevice(c->device));
@@ -513,7 +519,7 @@ GM2_API int gm2_set_forced(gm2_ctx* c, const uint32_t* force_keep, const uint32_
     }
     c->planned = false; c->host_plan = false;
     return GM2_OK;
-}
+} GM2_CATCH(c, "gm2_set_forced")
 
 GM2_API int gm2_load_probs_dev(gm2_ctx* c, const float* probs, int64_t S, int64_t ld, float threshold) {
     int rc = begin_samples(c, S, "gm2_load_probs_dev"); if (rc) return rc;
@@ -620,7 +626,7 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
     return GM2_OK;
 }
 
-static int pull_plan(gm2_ctx* c) {
+static int pull_plan(gm2_ctx* c) try {
     if (!c->planned) return fail(c, GM2_ERR_STATE, "no plan: call gm2_plan first");
     if (c->host_plan) return GM2_OK;
     const int64_t S = c->S;
@@ -637,7 +643,7 @@ static int pull_plan(gm2_ctx* c) {
     CU(c, cudaStreamSynchronize(c->stream));
     c->host_plan = true;
     return GM2_OK;
-}
+} GM2_CATCH(c, "pull_plan")
 
 GM2_API int gm2_plan(gm2_ctx* c, int64_t first_idx) {
     int rc = gm2_plan_async(c, first_idx); if (rc) return rc;
@@ -840,7 +846,7 @@ GM2_API int gm2_diag_fill(gm2_ctx* c, uint8_t* dev, int64_t bytes, uint32_t patt
 // Hashes of the minimized SEQUENCES (bases only, no header / newline) of records [s0,s1), computed
 // on the device from staged emits: backs the reference's duplicate report
 // (check_sequence_duplicates, minimizer_2.py:273-303) without moving any base to the host.
-GM2_API int gm2_sequence_hashes(gm2_ctx* c, int64_t s0, int64_t s1, uint64_t* out) {
+GM2_API int gm2_sequence_hashes(gm2_ctx* c, int64_t s0, int64_t s1, uint64_t* out) try {
     if (!c) return GM2_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
     int rc = pull_plan(c); if (rc) return rc;
@@ -886,7 +892,7 @@ GM2_API int gm2_sequence_hashes(gm2_ctx* c, int64_t s0, int64_t s1, uint64_t* ou
         a = b;
     }
     return GM2_OK;
-}
+} GM2_CATCH(c, "gm2_sequence_hashes")
 
 GM2_API int gm2_diag_fill_streams(gm2_ctx* c, uint8_t* dev, int64_t nrec, int64_t stride, int32_t ntile, int64_t chunk,
                                   int32_t batch, int32_t warps, int32_t order, int32_t vec32)
@@ -902,7 +908,7 @@ GM2_API int gm2_diag_fill_streams(gm2_ctx* c, uint8_t* dev, int64_t nrec, int64_
 
 GM2_API int gm2_diag_range_hashes(gm2_ctx* c, const uint8_t* dev, int64_t dev_bytes, const int64_t* off,
                                   int64_t n, uint64_t* out)
-{
+try {
     if (!c || n < 0 || (n > 0 && (!dev || !off || !out)) || ((uintptr_t)dev & 7))
         return fail(c, GM2_ERR_INVALID, "gm2_diag_range_hashes: bad arguments (8-byte aligned pointer required)");
     if (n == 0) return GM2_OK;
@@ -932,7 +938,7 @@ GM2_API int gm2_diag_range_hashes(gm2_ctx* c, const uint8_t* dev, int64_t dev_by
     }
     cudaFree(d_off); cudaFree(d_out);
     return rc;
-}
+} GM2_CATCH(c, "gm2_diag_range_hashes")
 
 
 // ------------------------------------------------------------------------------------------
