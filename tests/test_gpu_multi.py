@@ -29,9 +29,17 @@ def _worker(rank, world, port, case_name, out_path, ret_path):
             fh.write(case["genbank"])
         rec = genbank.read_genbank(fh.name)
         os.unlink(fh.name)
+        lists = case["lists"]
+        if case_name in ("hundred_and_one", "medium_k12"):
+            # the way a driver script gets them: the .npy file, tokenised natively, sliced per rank
+            from genome_minimizer_2_b200 import engine, synth
+            npy = f"{ret_path}.lists.{rank}.npy"
+            synth.save_gene_lists(npy, lists)
+            lists = engine.load_gene_lists(npy, engine.GeneTable.from_record(rec))
+            assert isinstance(lists, engine.TokenizedLists)
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
-            ret = gdist.run_single_file_sharded(rec, case["lists"], case["model_name"], out_path, timestamp="<TS>")
+            ret = gdist.run_single_file_sharded(rec, lists, case["model_name"], out_path, timestamp="<TS>")
         with open(f"{ret_path}.{rank}", "w") as fh:
             json.dump({"ret": ret, "stdout": buf.getvalue()}, fh)
     finally:
