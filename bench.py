@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--store-policy", type=int, default=-1)
     ap.add_argument("--packing", type=int, default=0)
     ap.add_argument("--emit-order", type=int, default=-1)
+    ap.add_argument("--wire", type=int, default=-1, help="GM2_CFG_WIRE for the e2e leg (0 auto, 1 bytes, 2 two-bit)")
+    ap.add_argument("--host-threads", type=int, default=-1, help="GM2_CFG_HOST_THREADS")
     ap.add_argument("--flat-run-bytes", type=int, default=-1, help="GM2_CFG_FLAT_RUN_BYTES (0 never, 1048576 always)")
     ap.add_argument("--emit-debug", type=int, default=0, help="timing experiments only (wrong output)")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -375,6 +377,10 @@ def main():
         ctx.configure(_native.CFG_ORDER, args.emit_order)
     if args.flat_run_bytes >= 0:
         ctx.configure(_native.CFG_FLAT_RUN_BYTES, args.flat_run_bytes)
+    if args.wire >= 0:
+        ctx.configure(_native.CFG_WIRE, args.wire)
+    if args.host_threads >= 0:
+        ctx.configure(_native.CFG_HOST_THREADS, args.host_threads)
     if args.emit_debug:
         ctx.configure(_native.CFG_DEBUG, args.emit_debug)
         args.verify = 0
@@ -538,10 +544,25 @@ def main():
             le, ro = ctx.minimize_host(pinned, ids=ids_e, off=off_e, first_idx=first_idx)
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
+        wire_used = ctx.query(_native.Q_LAST_WIRE)
+        d2h_moved = ctx.query(_native.Q_LAST_D2H_BYTES)
+        # the other transport beside it (image bytes over PCIe), one warm-up + one timed call
+        dt_bytes = None
+        if wire_used == 2:
+            ctx.configure(_native.CFG_WIRE, 1)
+            ctx.minimize_host(pinned, ids=ids_e, off=off_e, first_idx=first_idx)
+            barrier()
+            t0 = time.perf_counter()
+            ctx.minimize_host(pinned, ids=ids_e, off=off_e, first_idx=first_idx)
+            barrier()
+            dt_bytes = time.perf_counter() - t0
+            ctx.configure(_native.CFG_WIRE, args.wire if args.wire >= 0 else 0)
+            le, ro = ctx.minimize_host(pinned, ids=ids_e, off=off_e, first_idx=first_idx)   # the checked image is the default path's
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, dt_bytes or 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt = float(t[0].item())
+            dt_bytes = float(t[1].item()) or None
             kb = torch.tensor([int(le.sum())], dtype=torch.int64, device=dev)
             dist.all_reduce(kb, op=dist.ReduceOp.SUM)
             kept_e = int(kb.item())
@@ -559,11 +580,17 @@ def main():
             raise SystemExit("bench.py: e2e host image differs from the oracle")
         e2e = {"value": kept_e / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(ids_e.nbytes + off_e.nbytes),
-               "d2h_bytes_per_step": int(e_bytes + le.nbytes + ro.nbytes),
+               "d2h_bytes_per_step": int(d2h_moved + le.nbytes + ro.nbytes),
                "ms_per_step": dt * 1e3, "samples_per_step": S_e,
-               "achieved_d2h_gbs_per_gpu": e_bytes / dt / 1e9,
+               "image_bytes_per_step": e_bytes,
+               "delivered_image_gbs_per_gpu": e_bytes / dt / 1e9,
                "raw_pinned_d2h_gbs_per_gpu": raw_gbs,
-               "note": "PCIe/host-memory bound: compare achieved with raw (plain pinned cudaMemcpy, all ranks concurrently)",
+               "transport": ("two bits per base over PCIe (k_emit_packed), expanded into the caller's buffer by host threads"
+                             if wire_used == 2 else "image bytes over PCIe (k_emit)"),
+               "image_bytes_transport": (None if dt_bytes is None else
+                                         {"value": kept_e / dt_bytes / 1e9, "ms_per_step": dt_bytes * 1e3,
+                                          "delivered_image_gbs_per_gpu": e_bytes / dt_bytes / 1e9}),
+               "note": "raw = plain pinned cudaMemcpy of image-sized data, all ranks concurrently: the ceiling of the image-bytes transport",
                "api": "gm2_minimize_host (C-ABI): host id lists in, pinned host FASTA image out"}
         pinned.free()
 

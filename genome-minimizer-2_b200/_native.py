@@ -18,8 +18,8 @@ ABI_VERSION = 1
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY, CFG_RUN_TABLE, CFG_DEBUG, CFG_ORDER = 1, 2, 3, 4, 5, 6, 7, 8
-CFG_FLAT_RUN_BYTES = 9
-Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS = 1, 2, 3, 4, 5, 6, 7
+CFG_FLAT_RUN_BYTES, CFG_WIRE, CFG_HOST_THREADS = 9, 10, 11
+Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS, Q_LAST_WIRE, Q_LAST_D2H_BYTES = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 _c = ctypes
 _P = _c.c_void_p
@@ -64,6 +64,7 @@ SIGNATURES = {
     "gm2_diag_fill": (_c.c_int, [_P, _P, _I64, _c.c_uint32]),
     "gm2_diag_fill_streams": (_c.c_int, [_P, _P, _I64, _I64, _c.c_int32, _I64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
     "gm2_diag_range_hashes": (_c.c_int, [_P, _P, _I64, _P, _I64, _P]),
+    "gm2_diag_expand": (_c.c_int, [_P, _P, _P, _P, _I64, _c.c_int32, _I64, _c.c_char_p, _P, _c.c_int32, _c.c_int32]),
     "gm2_tokenize_pickle": (_c.c_int, [_P, _I64, _I64, _I64, _P, _P, _c.c_int32, _P, _I64, _P, _P]),
 }
 

@@ -9,6 +9,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "gm2.cu")
+HOST_SRC = [os.path.join(PKG_DIR, "csrc", "host_expand.cpp")]      # host-only C++, compiled by nvcc's host compiler
 HDR = os.path.join(REPO_ROOT, "include", "gm2.h")
 LIB = os.path.join(PKG_DIR, "libgm2.so")
 
@@ -33,14 +34,14 @@ def is_stale() -> bool:
         return True
     t = os.path.getmtime(LIB)
     csrc = os.path.dirname(SRC)
-    deps = [HDR] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    deps = [HDR] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cpp", ".hpp"))]
     return any(os.path.getmtime(p) > t for p in deps)
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_ROOT, "include"), "-o", LIB, SRC]
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_ROOT, "include"), "-o", LIB, SRC, *HOST_SRC]
     if os.environ.get("GM2_EMIT_DEBUG"):          # timing knock-outs in k_emit (wrong output): experiments only
         cmd.insert(1, "-DGM2_EMIT_DEBUG")
     if verbose:

@@ -28,6 +28,7 @@
 
 #include "gm2.h"
 #include "host_tokenize.hpp"
+#include "host_expand.hpp"
 
 #define GM2_API extern "C" __attribute__((visibility("default")))
 
@@ -39,6 +40,7 @@
 #include "k2_plan.cuh"
 #include "k3_scan.cuh"
 #include "k4_emit.cuh"
+#include "k5_emit_packed.cuh"
 #include "diag.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -67,6 +69,8 @@ struct gm2_ctx {
     int rt_cap = 64;
     int debug = 0;
     int order = 1;
+    int wire = 0;                  // gm2_emit_host transport: 0 auto, 1 bytes, 2 two-bit + host expansion
+    int host_threads = 0;          // host expansion threads (0: hardware threads / LOCAL_WORLD_SIZE)
     int flat_run_bytes = 640;      // see emit_runs_flat; measured crossover in profiles/r01_emit_experiments.md
     HeaderPrefix prefix;
 
@@ -76,6 +80,7 @@ struct gm2_ctx {
     int32_t F = 0, FW = 0;
     int ntiles = 0, nseg = 0, nslots = 0, SW = 0, max_tile_slots = 0;
     int packing = 1;
+    bool acgt_only = false;            // the reference holds nothing but upper-case A, C, G, T (two-bit forms usable)
     uint8_t* d_seq = nullptr;
     uint8_t* d_seq2 = nullptr;         // 2 bits per base (only when packing == 2)
     int32_t *d_tile_slot = nullptr, *d_slot_src = nullptr, *d_slot_len = nullptr;
@@ -113,6 +118,12 @@ struct gm2_ctx {
 
     // staging for gm2_emit_host
     uint8_t* d_stage[2] = {nullptr, nullptr}; int64_t stage_cap = 0;
+    // two-bit wire format (k_emit_packed -> pinned host staging -> host_expand): device / pinned words, tile_off rows
+    uint32_t* d_pstage[2] = {nullptr, nullptr}; uint32_t* h_pstage[2] = {nullptr, nullptr}; int64_t pstage_words = 0;
+    int32_t* h_toff[2] = {nullptr, nullptr}; int64_t h_toff_cap = 0;
+    gm2host::Pool* pool = nullptr;     // expansion workers, created on first use
+    int64_t last_d2h_bytes = 0;        // device->host bytes moved by the last gm2_emit_host
+    int last_wire = 1;                 // wire format it used
     // scratch for diag hashes
 };
 
@@ -226,6 +237,12 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     for (void* p : frees) if (p) cudaFree(p);
     if (c->h_len) cudaFreeHost(c->h_len);
     if (c->h_rec_off) cudaFreeHost(c->h_rec_off);
+    delete c->pool;
+    for (int i = 0; i < 2; ++i) {
+        if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
+        if (c->h_pstage[i]) cudaFreeHost(c->h_pstage[i]);
+        if (c->h_toff[i]) cudaFreeHost(c->h_toff[i]);
+    }
     for (int i = 0; i < 2; ++i) {
         if (c->ev_emit[i]) cudaEventDestroy(c->ev_emit[i]);
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -263,6 +280,12 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     case GM2_CFG_FLAT_RUN_BYTES:
         if (value < 0 || value > (1 << 20)) return fail(c, GM2_ERR_INVALID, "flat run bytes must be in 0..1048576");
         c->flat_run_bytes = (int)value; return GM2_OK;
+    case GM2_CFG_WIRE:
+        if (value < 0 || value > 2) return fail(c, GM2_ERR_INVALID, "wire must be 0 (auto), 1 (bytes) or 2 (two-bit)");
+        c->wire = (int)value; return GM2_OK;
+    case GM2_CFG_HOST_THREADS:
+        if (value < 0 || value > 256) return fail(c, GM2_ERR_INVALID, "host threads must be in 0..256");
+        c->host_threads = (int)value; return GM2_OK;
     case GM2_CFG_DEBUG:
         c->debug = (int)value; return GM2_OK;
     case GM2_CFG_RUN_TABLE:
@@ -283,6 +306,8 @@ GM2_API int gm2_query(const gm2_ctx* c, int key, int64_t* out) {
     case GM2_Q_PACKING:      *out = c->packing; return GM2_OK;
     case GM2_Q_NUM_SLOTS:    *out = c->nslots; return GM2_OK;
     case GM2_Q_KEEP_WORDS:   *out = c->FW; return GM2_OK;
+    case GM2_Q_LAST_WIRE:    *out = c->last_wire; return GM2_OK;
+    case GM2_Q_LAST_D2H_BYTES: *out = c->last_d2h_bytes; return GM2_OK;
     default: return GM2_ERR_INVALID;
     }
 }
@@ -410,19 +435,24 @@ try {
     c->ntiles = ntiles; c->nseg = nseg; c->nslots = (int)slot_src.size(); c->SW = c->nslots / 32;
     c->packing = 1; c->max_tile_slots = max_tile_slots;
     if (c->d_seq2) { cudaFree(c->d_seq2); c->d_seq2 = nullptr; }
-    if (c->packing_req == 2) {
-        // measured slower than bytes (profiles/r01_emit_experiments.md) — kept as a selectable form
+    {
+        // two bits per base, for k_emit<.,.,2> (GM2_CFG_PACKING 2: measured slower than bytes,
+        // profiles/r01_emit_experiments.md, kept selectable) and for the two-bit wire format of gm2_emit_host
+        bool acgt = true;
         std::vector<uint8_t> packed((size_t)ntiles * (size_t)(T / 4) + 256, 0);
-        for (int64_t i = 0; i < G; ++i) {
-            uint8_t code;
+        for (int64_t i = 0; i < G && acgt; ++i) {
+            uint8_t code = 0;
             switch (seq[i]) {
             case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
-            default: return fail(c, GM2_ERR_INVALID, "gm2_set_reference: two-bit packing needs an upper-case ACGT-only sequence");
+            default: acgt = false;
             }
             packed[(size_t)(i >> 2)] |= (uint8_t)(code << (2 * (i & 3)));
         }
-        if ((rc = dev_upload(c, &c->d_seq2, packed))) return rc;
-        c->packing = 2;
+        c->acgt_only = acgt && G > 0;
+        if (c->packing_req == 2 && !acgt)
+            return fail(c, GM2_ERR_INVALID, "gm2_set_reference: two-bit packing needs an upper-case ACGT-only sequence");
+        if (acgt) { if ((rc = dev_upload(c, &c->d_seq2, packed))) return rc; }
+        if (c->packing_req == 2) c->packing = 2;
     }
     c->have_ref = true; c->planned = false; c->host_plan = false; c->mode = 0; c->S = 0;
     return GM2_OK;
@@ -742,6 +772,115 @@ GM2_API int gm2_emit_dev(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out, i
     return launch_emit(c, s0, s1, dev_out);
 }
 
+// ---- two-bit wire format for the host path (k5_emit_packed.cuh, host_expand.cpp) ------------------
+static int64_t env_i64(const char* name, int64_t dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long long v = atoll(e);
+    return v > 0 ? (int64_t)v : dflt;
+}
+
+static inline int64_t packed_words(const gm2_ctx* c, int64_t a, int64_t b) {
+    return ((c->h_rec_off[b] - c->h_rec_off[a]) >> 4) + (b - a) * (int64_t)(c->ntiles + 2) + 8;
+}
+
+static int launch_emit_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint32_t* dev_out) {
+    const int64_t n = s1 - s0;
+    if (n <= 0) return GM2_OK;
+    const int warps = c->emit_warps;
+    int64_t batch = c->emit_batch;
+    if (batch <= 0) {
+        const int64_t want_ctas = (int64_t)c->sm_count * 8;
+        batch = (n * c->ntiles + want_ctas - 1) / want_ctas;
+        batch = std::max<int64_t>(batch, warps);
+        batch = std::min<int64_t>(batch, 64);
+        batch = ((batch + warps - 1) / warps) * warps;
+    }
+    const int64_t nbatch = (n + batch - 1) / batch;
+    const int64_t blocks = nbatch * c->ntiles;
+    if (blocks > 0x7fffffffLL) return fail(c, GM2_ERR_INVALID, "gm2_emit_host: grid too large; use a smaller chunk");
+    PackedParams p;
+    p.seq2 = c->d_seq2; p.tile_slot = c->d_tile_slot; p.slot_src = c->d_slot_src; p.slot_len = c->d_slot_len;
+    p.segkept = c->d_segkept; p.tile_off = c->d_tile_off; p.rec_off = c->d_rec_off; p.out = dev_out;
+    p.s0 = s0; p.s1 = s1; p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW;
+    p.batch = (int)batch; p.nbatch = (int)nbatch; p.rt_cap = c->rt_cap;
+    p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;
+    p.order = c->order;
+    const size_t sm = 32 + (size_t)(c->tile_bytes / 4) + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 8;
+    if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit_host: shared memory budget exceeded; lower tile bytes / emit warps");
+    CU(c, cudaFuncSetAttribute(k_emit_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_emit_packed<<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
+    LAUNCH_CHECK(c, "k_emit_packed");
+    return GM2_OK;
+}
+
+static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_out, int64_t chunk_bytes) try {
+    const int nt = c->ntiles;
+    const int threads = c->host_threads > 0 ? c->host_threads : gm2host::default_threads();
+    if (!c->pool || c->pool->threads() != threads) { delete c->pool; c->pool = nullptr; c->pool = new gm2host::Pool(threads); }
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    int64_t max_words = 0, max_rows = 0;
+    for (int64_t a = s0; a < s1;) {
+        int64_t b = a + 1;
+        while (b < s1 && c->h_rec_off[b + 1] - c->h_rec_off[a] <= chunk_bytes) ++b;
+        chunks.emplace_back(a, b);
+        max_words = std::max(max_words, packed_words(c, a, b));
+        max_rows = std::max(max_rows, b - a);
+        a = b;
+    }
+    if (max_words > c->pstage_words) {
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
+            if (c->h_pstage[i]) cudaFreeHost(c->h_pstage[i]);
+            c->d_pstage[i] = nullptr; c->h_pstage[i] = nullptr;
+        }
+        c->pstage_words = 0;
+        for (int i = 0; i < 2; ++i) {
+            CU(c, cudaMalloc((void**)&c->d_pstage[i], (size_t)max_words * 4));
+            CU(c, cudaMallocHost((void**)&c->h_pstage[i], (size_t)max_words * 4 + 64));    // + the decoder's over-read
+        }
+        c->pstage_words = max_words;
+    }
+    if (max_rows * nt > c->h_toff_cap) {
+        for (int i = 0; i < 2; ++i) { if (c->h_toff[i]) cudaFreeHost(c->h_toff[i]); c->h_toff[i] = nullptr; }
+        c->h_toff_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(c, cudaMallocHost((void**)&c->h_toff[i], (size_t)(max_rows * nt) * 4));
+        c->h_toff_cap = max_rows * nt;
+    }
+    auto expand = [&](size_t i) -> int {
+        const int buf = (int)(i & 1);
+        CU(c, cudaEventSynchronize(c->ev_copy[buf]));
+        gm2host::ChunkView v;
+        v.packed = c->h_pstage[buf]; v.tile_off = c->h_toff[buf]; v.rec_off = c->h_rec_off; v.lengths = c->h_len;
+        v.out = host_out + (c->h_rec_off[chunks[i].first] - c->h_rec_off[s0]);
+        v.s0 = chunks[i].first; v.s1 = chunks[i].second; v.first_idx = c->first_idx; v.ntiles = nt;
+        v.prefix = c->prefix.text; v.prefix_len = c->prefix.len; v.simd = true;
+        c->pool->expand_chunk(v);
+        return GM2_OK;
+    };
+    int rc;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        const int buf = (int)(i & 1);
+        const int64_t a = chunks[i].first, b = chunks[i].second;
+        // d_pstage[buf] / h_pstage[buf] were last used by chunk i-2: its copy is ordered by the event, its
+        // expansion finished on this thread before chunk i-1 was launched
+        if (i >= 2) CU(c, cudaStreamWaitEvent(c->stream, c->ev_copy[buf], 0));
+        if ((rc = launch_emit_packed(c, a, b, c->d_pstage[buf]))) return rc;
+        CU(c, cudaEventRecord(c->ev_emit[buf], c->stream));
+        CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_emit[buf], 0));
+        const int64_t words = packed_words(c, a, b), rows = (b - a) * nt;
+        CU(c, cudaMemcpyAsync(c->h_pstage[buf], c->d_pstage[buf], (size_t)words * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->h_toff[buf], c->d_tile_off + (size_t)a * nt, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(c, cudaEventRecord(c->ev_copy[buf], c->copy_stream));
+        c->last_d2h_bytes += words * 4 + rows * 4;
+        if (i >= 1 && (rc = expand(i - 1))) return rc;
+    }
+    if (!chunks.empty() && (rc = expand(chunks.size() - 1))) return rc;
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return GM2_OK;
+} GM2_CATCH(c, "gm2_emit_host")
+
 GM2_API int gm2_emit_host(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_out, int64_t cap, int64_t chunk_bytes) {
     if (!c) return GM2_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
@@ -750,7 +889,21 @@ GM2_API int gm2_emit_host(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_out,
     const int64_t total = c->h_rec_off[s1] - c->h_rec_off[s0];
     if (total > cap) return fail(c, GM2_ERR_CAPACITY, "gm2_emit_host: output buffer too small");
     if (total > 0 && !host_out) return fail(c, GM2_ERR_INVALID, "gm2_emit_host: host_out is NULL");
-    if (chunk_bytes <= 0) chunk_bytes = (int64_t)256 << 20;
+    const bool default_chunk = chunk_bytes <= 0;
+    if (default_chunk) chunk_bytes = (int64_t)256 << 20;
+    c->last_d2h_bytes = 0; c->last_wire = 1;
+    if (c->wire == 2 && !c->acgt_only)
+        return fail(c, GM2_ERR_STATE, "gm2_emit_host: the two-bit wire format needs an ACGT-only reference (GM2_CFG_WIRE)");
+    // auto: expansion needs ~6 threads to beat the plain copy of one GPU (measured: 50 / 77 / 98 Gbp/s with
+    // 4 / 8 / 16 threads against 55 for the copy); with fewer (many ranks sharing the host) the copy is as good
+    if (total > 0 && (c->wire == 2 || (c->wire == 0 && c->acgt_only &&
+                                       (c->host_threads > 0 ? c->host_threads : gm2host::default_threads()) >= 6))) {
+        c->last_wire = 2;
+        // smaller pieces by default: the copy of piece i+1 hides under the expansion of piece i, also when the
+        // caller asks for one 256 MB range at a time (engine.drain)
+        return emit_host_packed(c, s0, s1, host_out, default_chunk ? env_i64("GM2_WIRE_CHUNK_BYTES", (int64_t)64 << 20) : chunk_bytes);
+    }
+    c->last_d2h_bytes = total;
     // staging must hold the largest single record of the range
     int64_t need = std::min(chunk_bytes, total);
     for (int64_t s = s0; s < s1; ++s) need = std::max(need, c->h_rec_off[s + 1] - c->h_rec_off[s]);
@@ -990,4 +1143,23 @@ GM2_API int gm2_tokenize_pickle(const uint8_t* body, int64_t nbytes, int64_t S, 
     } catch (const std::bad_alloc&) {
         return fail(nullptr, GM2_ERR_NOMEM, "gm2_tokenize_pickle: out of host memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-only: the decoder of the two-bit wire format on caller-supplied data (tests, probes)
+// ------------------------------------------------------------------------------------------
+GM2_API int gm2_diag_expand(const uint32_t* packed, const int32_t* tile_off, const int64_t* rec_off,
+                            const int64_t* lengths, int64_t S, int32_t ntiles, int64_t first_idx,
+                            const char* prefix, uint8_t* out, int32_t threads, int32_t simd) {
+    if (S < 0 || ntiles <= 0 || !prefix || (S > 0 && (!packed || !tile_off || !rec_off || !lengths || !out)))
+        return fail(nullptr, GM2_ERR_INVALID, "gm2_diag_expand: bad argument");
+    const size_t n = strlen(prefix);
+    if (n > GM2_MAX_PREFIX - 1) return fail(nullptr, GM2_ERR_INVALID, "gm2_diag_expand: prefix too long");
+    std::string full = ">" + std::string(prefix);
+    gm2host::ChunkView v;
+    v.packed = packed; v.tile_off = tile_off; v.rec_off = rec_off; v.lengths = lengths; v.out = out;
+    v.s0 = 0; v.s1 = S; v.first_idx = first_idx; v.ntiles = ntiles;
+    v.prefix = full.c_str(); v.prefix_len = (int)full.size(); v.simd = simd != 0;
+    gm2host::expand_chunk(v, threads > 0 ? threads : gm2host::default_threads());
+    return GM2_OK;
 }

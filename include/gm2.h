@@ -57,6 +57,10 @@ extern "C" {
 #define GM2_CFG_FLAT_RUN_BYTES 9 /* (sample, tile) batches whose mean kept-run length is below this many bytes use the
                                     vector-per-lane emit path instead of the run-by-run stream; 0 = never, 1048576 = always
                                     (default 640; byte packing only) */
+#define GM2_CFG_WIRE          10 /* transport of gm2_emit_host / gm2_minimize_host: 0 auto (two-bit when the reference is
+                                    ACGT-only and >= 6 host threads are available), 1 image bytes over PCIe,
+                                    2 two bits per base over PCIe + expansion by host threads (error if not ACGT-only) */
+#define GM2_CFG_HOST_THREADS  11 /* host threads for that expansion; 0 = hardware threads / LOCAL_WORLD_SIZE */
 #define GM2_CFG_DEBUG         7  /* timing knock-outs (WRONG output); only effective in -DGM2_EMIT_DEBUG builds */
 
 /* gm2_query keys */
@@ -67,6 +71,8 @@ extern "C" {
 #define GM2_Q_PACKING         5  /* packing actually in use (1 or 2)        */
 #define GM2_Q_NUM_SLOTS       6
 #define GM2_Q_KEEP_WORDS      7  /* 32-bit words per keep row = ceil(F/32)  */
+#define GM2_Q_LAST_WIRE       8  /* wire format the last gm2_emit_host used (1 or 2) */
+#define GM2_Q_LAST_D2H_BYTES  9  /* device->host bytes the last gm2_emit_host moved  */
 
 typedef struct gm2_ctx gm2_ctx;
 
@@ -157,7 +163,10 @@ int gm2_emit_dev(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* dev_out, int64_t
 /* Same, delivered to CPU memory: records [s0,s1) are produced in device staging
  * buffers in pieces of about `chunk_bytes` (0 = default) and copied to `host_out`
  * while the next piece is being produced.  Synchronous.  `host_out` should be pinned
- * (gm2_host_alloc) for full PCIe speed. */
+ * (gm2_host_alloc) for full PCIe speed.  Transport (GM2_CFG_WIRE): either the finished image bytes
+ * are copied, or — ACGT-only reference — the kept bases cross PCIe as 2 bits each and host threads
+ * (GM2_CFG_HOST_THREADS) expand them into `host_out`, headers and newlines included; the bytes in
+ * `host_out` are the same.  chunk_bytes 0 = default (256 MiB for the copy, 64 MiB for two-bit). */
 int gm2_emit_host(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* host_out, int64_t cap,
                   int64_t chunk_bytes);
 
@@ -217,6 +226,16 @@ int gm2_diag_range_hashes(gm2_ctx* ctx, const uint8_t* dev, int64_t dev_bytes,
 int gm2_tokenize_pickle(const uint8_t* body, int64_t nbytes, int64_t S, int64_t L,
                         const char* names, const int64_t* name_off, int32_t V,
                         int32_t* ids_out, int64_t ids_cap, int64_t* off_out, int64_t* count_out);
+
+/* Host only.  Decoder of the two-bit wire format gm2_emit_host uses internally (GM2_CFG_WIRE), on
+ * caller-supplied data: S records whose kept bases arrive as per-(sample, tile) 2-bit pieces; piece
+ * (i, t) starts at 32-bit word (rec_off[i] >> 4) + i * (ntiles + 2) + (tile_off[i][t] >> 4) + t of
+ * `packed` (rec_off[0] == 0), base j in bits [2j, 2j+2), codes 0..3 = A C G T.  Writes the records
+ * ('>' + prefix + (first_idx + i + 1) + '\n' + bases + '\n') at out + rec_off[i].  `packed` must be
+ * readable 16 bytes past its last used word.  threads 0 = default; simd 0 = portable scalar decoder. */
+int gm2_diag_expand(const uint32_t* packed, const int32_t* tile_off, const int64_t* rec_off,
+                    const int64_t* lengths, int64_t S, int32_t ntiles, int64_t first_idx,
+                    const char* prefix, uint8_t* out, int32_t threads, int32_t simd);
 
 #ifdef __cplusplus
 }

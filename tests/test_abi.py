@@ -37,14 +37,16 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_header_constants_match_binding():
     text = open(os.path.join(ROOT, "include", "gm2.h")).read()
-    consts = dict(re.findall(r"#define\s+(GM2_[A-Z_]+)\s+(-?\d+)", text))
+    consts = dict(re.findall(r"#define\s+(GM2_[A-Z0-9_]+)\s+(-?\d+)", text))
     assert int(consts["GM2_ABI_VERSION"]) == _native.ABI_VERSION
     for k, v in (("GM2_ERR_INVALID", _native.ERR_INVALID), ("GM2_ERR_CUDA", _native.ERR_CUDA),
                  ("GM2_ERR_STATE", _native.ERR_STATE), ("GM2_ERR_CAPACITY", _native.ERR_CAPACITY),
                  ("GM2_ERR_NOMEM", _native.ERR_NOMEM), ("GM2_ERR_UNSUPPORTED", _native.ERR_UNSUPPORTED), ("GM2_CFG_TILE_BYTES", _native.CFG_TILE_BYTES),
                  ("GM2_CFG_EMIT_WARPS", _native.CFG_EMIT_WARPS), ("GM2_CFG_EMIT_BATCH", _native.CFG_EMIT_BATCH),
                  ("GM2_CFG_PACKING", _native.CFG_PACKING), ("GM2_CFG_STORE_POLICY", _native.CFG_STORE_POLICY),
-                 ("GM2_CFG_FLAT_RUN_BYTES", _native.CFG_FLAT_RUN_BYTES), ("GM2_CFG_ORDER", _native.CFG_ORDER),
+                 ("GM2_CFG_FLAT_RUN_BYTES", _native.CFG_FLAT_RUN_BYTES), ("GM2_CFG_WIRE", _native.CFG_WIRE),
+                 ("GM2_CFG_HOST_THREADS", _native.CFG_HOST_THREADS), ("GM2_Q_LAST_WIRE", _native.Q_LAST_WIRE),
+                 ("GM2_Q_LAST_D2H_BYTES", _native.Q_LAST_D2H_BYTES), ("GM2_CFG_ORDER", _native.CFG_ORDER),
                  ("GM2_Q_LAUNCHES", _native.Q_LAUNCHES), ("GM2_Q_KEEP_WORDS", _native.Q_KEEP_WORDS)):
         assert int(consts[k]) == v, k
 

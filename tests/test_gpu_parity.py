@@ -96,10 +96,25 @@ def _oracle_image(seq, starts, ends, rows, first_idx=0):
 
 
 def _gpu_image(ctx, S):
+    """The image through gm2_emit_host, by BOTH transports when the reference allows it: image bytes
+    over PCIe (k_emit) and two bits per base + host expansion (k_emit_packed, GM2_CFG_WIRE)."""
     n = ctx.image_bytes(0, S)
-    out = np.empty(n, dtype=np.uint8)
-    ctx.emit_host(0, S, out)
-    return out
+    outs = []
+    for wire in (1, 2):
+        ctx.configure(_native.CFG_WIRE, wire)
+        out = np.full(n, 0x2a, dtype=np.uint8)
+        try:
+            ctx.emit_host(0, S, out)
+        except _native.Gm2Error as e:
+            if wire == 2 and e.code == _native.ERR_STATE:        # reference with letters other than ACGT
+                continue
+            raise
+        assert ctx.query(_native.Q_LAST_WIRE) == (wire if n else 1)
+        outs.append(out)
+    ctx.configure(_native.CFG_WIRE, 0)
+    if len(outs) == 2:
+        assert np.array_equal(outs[0], outs[1]), "the two transports disagree"
+    return outs[0]
 
 
 @pytest.mark.parametrize("G,F,seed,kw", [
@@ -297,7 +312,7 @@ def test_dense_tiny_genes_exercise_table_flush_and_global_slot_path():
     rng = np.random.default_rng(123)
     G = 70_000
     F = 6_000
-    seq = rng.integers(65, 91, G, dtype=np.uint8)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G)]        # ACGT: both transports are exercised
     starts = np.sort(rng.integers(0, G - 12, F)).astype(np.int64)
     ends = starts + rng.integers(1, 12, F)
     S = 21
@@ -536,6 +551,50 @@ def test_fuzz_kernel_configurations():
             ctx.plan(first)
             assert np.array_equal(ctx.lengths(), exp_len), (trial, cfg)
             assert np.array_equal(_gpu_image(ctx, S), exp_img), (trial, G, F, S, cfg)
+
+
+def test_wire_format_selection_and_threads():
+    """GM2_CFG_WIRE / GM2_CFG_HOST_THREADS: what gets chosen, what is refused, and that the number of
+    expansion threads does not change the bytes."""
+    rng = np.random.default_rng(77)
+    G, F, S = 150_000, 120, 37
+    starts = np.sort(rng.integers(0, G - 10, F)).astype(np.int64)
+    ends = starts + rng.integers(1, 2_500, F)
+    rows = synth.pack_keep_rows(rng.random((S, F)) < 0.5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G)]
+    iupac = acgt.copy()
+    iupac[1000] = ord("N")
+    for seq, is_acgt in ((acgt, True), (iupac, False)):
+        _, _, exp_img = _oracle_image(seq, starts, ends, rows, first_idx=5)
+        with _native.Context(0) as ctx:
+            ctx.configure(_native.CFG_TILE_BYTES, 16384)
+            ctx.set_reference(seq, starts, ends)
+            ctx.load_keep_host(rows)
+            ctx.plan(5)
+            n = ctx.image_bytes(0, S)
+            for wire, threads, want_wire in ((0, 8, 2 if is_acgt else 1), (0, 4, 1), (0, 1, 1), (1, 8, 1), (2, 1, 2), (2, 2, 2), (2, 5, 2), (2, 64, 2)):
+                ctx.configure(_native.CFG_WIRE, wire)
+                ctx.configure(_native.CFG_HOST_THREADS, threads)
+                out = np.zeros(n, dtype=np.uint8)
+                if wire == 2 and not is_acgt:
+                    with pytest.raises(_native.Gm2Error) as ei:
+                        ctx.emit_host(0, S, out)
+                    assert ei.value.code == _native.ERR_STATE
+                    continue
+                for chunk in (0, 1, 200_000):                       # default, one record per chunk, a few per chunk
+                    out[:] = 0
+                    ctx.emit_host(0, S, out, chunk_bytes=chunk)
+                    assert ctx.query(_native.Q_LAST_WIRE) == want_wire
+                    assert np.array_equal(out, exp_img), (is_acgt, wire, threads, chunk)
+                    d2h = ctx.query(_native.Q_LAST_D2H_BYTES)
+                    assert d2h == n if want_wire == 1 else 0 < d2h < n // 2
+            # a sub-range, two-bit
+            ctx.configure(_native.CFG_WIRE, 0)
+            ctx.configure(_native.CFG_HOST_THREADS, 3)
+            off = ctx.record_offsets()
+            part = np.zeros(int(off[30] - off[11]), dtype=np.uint8)
+            ctx.emit_host(11, 30, part)
+            assert np.array_equal(part, exp_img[int(off[11]):int(off[30])])
 
 
 def test_integration_md_ctypes_stub_runs_as_written(tmp_path):
