@@ -818,17 +818,22 @@ static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_ou
     const int nt = c->ntiles;
     const int threads = c->host_threads > 0 ? c->host_threads : gm2host::default_threads();
     if (!c->pool || c->pool->threads() != threads) { delete c->pool; c->pool = nullptr; c->pool = new gm2host::Pool(threads); }
+    // Chunks: at most chunk_bytes of image AND at most chunk_bytes/16 words of per-piece slack, so that the
+    // staging need is bounded by the chunk size alone (chunk_bytes/8 words, chunk_bytes/16 tile_off entries)
+    // and buffers sized once serve every later call; only a single record larger than that grows them.
     std::vector<std::pair<int64_t, int64_t>> chunks;
-    int64_t max_words = 0, max_rows = 0;
+    const int64_t slack_cap = std::max<int64_t>(chunk_bytes >> 4, 1);
+    int64_t max_words = (chunk_bytes >> 3) + 16, max_rows = slack_cap / (nt + 2) + 1;
     for (int64_t a = s0; a < s1;) {
         int64_t b = a + 1;
-        while (b < s1 && c->h_rec_off[b + 1] - c->h_rec_off[a] <= chunk_bytes) ++b;
+        while (b < s1 && c->h_rec_off[b + 1] - c->h_rec_off[a] <= chunk_bytes && (b + 1 - a) * (int64_t)(nt + 2) <= slack_cap) ++b;
         chunks.emplace_back(a, b);
         max_words = std::max(max_words, packed_words(c, a, b));
         max_rows = std::max(max_rows, b - a);
         a = b;
     }
     if (max_words > c->pstage_words) {
+        CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->copy_stream));
         for (int i = 0; i < 2; ++i) {
             if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
             if (c->h_pstage[i]) cudaFreeHost(c->h_pstage[i]);
@@ -842,6 +847,7 @@ static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_ou
         c->pstage_words = max_words;
     }
     if (max_rows * nt > c->h_toff_cap) {
+        CU(c, cudaStreamSynchronize(c->copy_stream));
         for (int i = 0; i < 2; ++i) { if (c->h_toff[i]) cudaFreeHost(c->h_toff[i]); c->h_toff[i] = nullptr; }
         c->h_toff_cap = 0;
         for (int i = 0; i < 2; ++i) CU(c, cudaMallocHost((void**)&c->h_toff[i], (size_t)(max_rows * nt) * 4));
@@ -899,9 +905,9 @@ GM2_API int gm2_emit_host(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_out,
     if (total > 0 && (c->wire == 2 || (c->wire == 0 && c->acgt_only &&
                                        (c->host_threads > 0 ? c->host_threads : gm2host::default_threads()) >= 6))) {
         c->last_wire = 2;
-        // smaller pieces by default: the copy of piece i+1 hides under the expansion of piece i, also when the
-        // caller asks for one 256 MB range at a time (engine.drain)
-        return emit_host_packed(c, s0, s1, host_out, default_chunk ? env_i64("GM2_WIRE_CHUNK_BYTES", (int64_t)64 << 20) : chunk_bytes);
+        // small pieces by default: the copy of piece i+1 hides under the expansion of piece i, and a caller that
+        // asks for one 256 MB range at a time (engine.drain) pays a short pipeline fill per call
+        return emit_host_packed(c, s0, s1, host_out, default_chunk ? env_i64("GM2_WIRE_CHUNK_BYTES", (int64_t)16 << 20) : chunk_bytes);
     }
     c->last_d2h_bytes = total;
     // staging must hold the largest single record of the range

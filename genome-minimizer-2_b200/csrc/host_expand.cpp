@@ -87,9 +87,9 @@ static int write_header(uint8_t* dst, const char* prefix, int prefix_len, unsign
     return prefix_len + nd + 1;
 }
 
-// One task = an eighth of one sample's tiles (finer than a sample so that the tail of a chunk does not
+// One task = a sixteenth of one sample's tiles (finer than a sample so that the tail of a chunk does not
 // leave threads idle); the first part also writes the header line, the last one the final newline.
-static const int TASKS_PER_SAMPLE = 8;
+static const int TASKS_PER_SAMPLE = 16;
 
 static void expand_task(const ChunkView& v, int64_t task) {
     const int64_t i = task / TASKS_PER_SAMPLE;

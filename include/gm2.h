@@ -166,7 +166,7 @@ int gm2_emit_dev(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* dev_out, int64_t
  * (gm2_host_alloc) for full PCIe speed.  Transport (GM2_CFG_WIRE): either the finished image bytes
  * are copied, or — ACGT-only reference — the kept bases cross PCIe as 2 bits each and host threads
  * (GM2_CFG_HOST_THREADS) expand them into `host_out`, headers and newlines included; the bytes in
- * `host_out` are the same.  chunk_bytes 0 = default (256 MiB for the copy, 64 MiB for two-bit). */
+ * `host_out` are the same.  chunk_bytes 0 = default (256 MiB for the copy, 16 MiB for two-bit). */
 int gm2_emit_host(gm2_ctx* ctx, int64_t s0, int64_t s1, uint8_t* host_out, int64_t cap,
                   int64_t chunk_bytes);
 
