@@ -900,10 +900,12 @@ GM2_API int gm2_emit_host(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_out,
     c->last_d2h_bytes = 0; c->last_wire = 1;
     if (c->wire == 2 && !c->acgt_only)
         return fail(c, GM2_ERR_STATE, "gm2_emit_host: the two-bit wire format needs an ACGT-only reference (GM2_CFG_WIRE)");
-    // auto: expansion needs ~6 threads to beat the plain copy of one GPU (measured: 50 / 77 / 98 Gbp/s with
-    // 4 / 8 / 16 threads against 55 for the copy); with fewer (many ranks sharing the host) the copy is as good
-    if (total > 0 && (c->wire == 2 || (c->wire == 0 && c->acgt_only &&
-                                       (c->host_threads > 0 ? c->host_threads : gm2host::default_threads()) >= 6))) {
+    // auto: a process alone on the host needs ~6 expansion threads to beat its plain copy (measured: 50 / 68 / 78 /
+    // 98 Gbp/s with 4 / 6 / 8 / 16 threads against 55 for the copy).  Several ranks on one host share its memory
+    // system, which caps their plain copies well below PCIe (17.6 GB/s per GPU at 4 ranks), and 4 threads each are
+    // enough (4 ranks: 105 Gbp/s two-bit against 69); with fewer threads per rank the plain copy is kept.
+    const int host_threads = c->host_threads > 0 ? c->host_threads : gm2host::default_threads();
+    if (total > 0 && (c->wire == 2 || (c->wire == 0 && c->acgt_only && host_threads >= (gm2host::local_ranks() > 1 ? 4 : 6)))) {
         c->last_wire = 2;
         // small pieces by default: the copy of piece i+1 hides under the expansion of piece i, and a caller that
         // asks for one 256 MB range at a time (engine.drain) pays a short pipeline fill per call

@@ -184,12 +184,15 @@ void expand_chunk(const ChunkView& v, int threads) {
     pool.expand_chunk(v);
 }
 
+int local_ranks() {
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int r = atoi(e); if (r > 1) return r; }
+    return 1;
+}
+
 int default_threads() {
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
-    int ranks = 1;
-    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int r = atoi(e); if (r > 1) ranks = r; }
-    int t = (int)hw / ranks;
+    int t = (int)hw / local_ranks();
     if (t < 1) t = 1;
     if (t > 32) t = 32;
     return t;

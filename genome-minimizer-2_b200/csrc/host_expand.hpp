@@ -48,7 +48,9 @@ private:
 };
 void expand_chunk(const ChunkView& v, int threads);
 
-// hardware threads / LOCAL_WORLD_SIZE (one process per GPU under torchrun), clamped to [1, 32]
+// processes sharing this host (LOCAL_WORLD_SIZE, as torchrun sets it; 1 when absent)
+int local_ranks();
+// hardware threads / local_ranks(), clamped to [1, 32]
 int default_threads();
 
 }  // namespace gm2host

@@ -58,7 +58,8 @@ extern "C" {
                                     vector-per-lane emit path instead of the run-by-run stream; 0 = never, 1048576 = always
                                     (default 640; byte packing only) */
 #define GM2_CFG_WIRE          10 /* transport of gm2_emit_host / gm2_minimize_host: 0 auto (two-bit when the reference is
-                                    ACGT-only and >= 6 host threads are available), 1 image bytes over PCIe,
+                                    ACGT-only and enough host threads are available: 6, or 4 per process when
+                                    LOCAL_WORLD_SIZE says several processes share the host), 1 image bytes over PCIe,
                                     2 two bits per base over PCIe + expansion by host threads (error if not ACGT-only) */
 #define GM2_CFG_HOST_THREADS  11 /* host threads for that expansion; 0 = hardware threads / LOCAL_WORLD_SIZE */
 #define GM2_CFG_DEBUG         7  /* timing knock-outs (WRONG output); only effective in -DGM2_EMIT_DEBUG builds */
