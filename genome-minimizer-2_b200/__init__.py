@@ -8,6 +8,7 @@ Layout
   genbank.py      restated `Bio.SeqIO.read(path, "genbank")` (Biopython is a reference dependency)
   minimizer_2.py  drop-in mirror of the reference module
                   src/genome_minimizer_2/minimizer/minimizer_2.py (same names, arguments, prints, returns)
+  reporting.py    the module's reporting helpers (duplicate statistics, summary file), host only
   synth.py        synthetic K-12-shaped GenBank + gene-list generator (the reference ships no data)
 
 Nothing here imports `oracle/`: the oracle is test infrastructure.
@@ -16,10 +17,16 @@ from .minimizer_2 import (  # noqa: F401
     GenomeMinimiser,
     process_multiple_genomes_single_file,
     process_multiple_genomes_multiple_files,
+    check_sequence_duplicates,
+    print_duplicate_statistics,
+    generate_summary_file,
 )
 
 __all__ = [
     "GenomeMinimiser",
     "process_multiple_genomes_single_file",
     "process_multiple_genomes_multiple_files",
+    "check_sequence_duplicates",
+    "print_duplicate_statistics",
+    "generate_summary_file",
 ]

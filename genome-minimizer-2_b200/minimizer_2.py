@@ -12,8 +12,9 @@ reference (minimizer_2.py:50-101) run as one batched job in libgm2.so on a B200.
 Preserved on purpose: records are never line-wrapped; the single-file
 preamble's third line is `np.datetime64('now')`; single-file averages add up only samples
 with idx<=9 or (idx+1)%100==0 yet divide by N; an empty `.npy` ends in ZeroDivisionError.
-Not provided: the plotting / duplicate-report helpers (reference :212-252, :273-444) — they
-are unreachable from the CLI and outside the hot path.
+The reporting helpers (reference :212-252, :273-444: `plot`, `check_sequence_duplicates`,
+`print_duplicate_statistics`, `generate_summary_file`) have no call sites in the reference; they
+are mirrored in `reporting.py` and re-exported here so every public name of the module exists.
 """
 from __future__ import annotations
 
@@ -24,6 +25,11 @@ import numpy as np
 
 from . import engine as _engine
 from .genbank import read_genbank
+from .reporting import (  # noqa: F401  (re-exported: reference :273-444)
+    check_sequence_duplicates,
+    generate_summary_file,
+    print_duplicate_statistics,
+)
 
 # default output root, the analogue of utils/directories.py:10 in the reference tree
 PROJECT_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -126,6 +132,34 @@ class GenomeMinimiser:
         os.makedirs(_default_dir(), exist_ok=True)
         with open(file_path, "w") as fh:            # header line + sequence, no trailing newline
             fh.write(f">{SEQ_ID_PREFIX}{self.idx+1}\n{self.reduced_genome_str}")
+
+    def plot(self):
+        """Histogram of minimized genome sizes (reference :212-252).  The reference never sets
+        `minimised_genomes_sizes`, so there as here this raises AttributeError unless the caller has
+        assigned it; with fewer than 100 values it only prints.  matplotlib is imported on use."""
+        sizes = self.minimised_genomes_sizes
+        if len(sizes) < 100:
+            print(f"Not enough data points ({len(sizes)}) to create meaningful plot. Need at least 100.")
+            return
+        print("Plotting reduced genomes size distribution graph...")
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        median = np.median(sizes)
+        fig = plt.figure(figsize=(4, 4))
+        plt.hist(sizes, bins=10, color="dodgerblue")
+        plt.xlabel("Genome size (Mbp)")
+        plt.ylabel("Frequency")
+        plt.title("Distribution of Minimized Genome Sizes")
+        plt.axvline(median, color="b", linestyle="dashed", linewidth=2, label=f"Median: {median:.2f}")
+        plt.legend(handles=[
+            plt.Line2D([], [], color="b", linestyle="dashed", linewidth=2, label=f"Median: {median:.2f}"),
+            plt.Line2D([], [], color="black", linewidth=2, label=f"Min: {np.min(sizes):.2f}"),
+            plt.Line2D([], [], color="black", linewidth=2, label=f"Max: {np.max(sizes):.2f}")])
+        os.makedirs(_default_dir(), exist_ok=True)
+        plt.savefig(os.path.join(_default_dir(), f"minimised_genomes_distribution_{self.model_name}.pdf"),
+                    format="pdf", bbox_inches="tight")
+        plt.close(fig)
 
     def get_reduction_stats(self) -> dict:
         n0, n1 = self.original_genome_length, len(self.reduced_genome_str)
