@@ -66,6 +66,10 @@ SIGNATURES = {
     "gm2_diag_range_hashes": (_c.c_int, [_P, _P, _I64, _P, _I64, _P]),
     "gm2_diag_expand": (_c.c_int, [_P, _P, _P, _P, _I64, _c.c_int32, _I64, _c.c_char_p, _P, _c.c_int32, _c.c_int32]),
     "gm2_tokenize_pickle": (_c.c_int, [_P, _I64, _I64, _I64, _P, _P, _c.c_int32, _P, _I64, _P, _P]),
+    "gm2_genbank_parse": (_c.c_int, [_P, _I64, _c.POINTER(_P)]),
+    "gm2_genbank_sizes": (_c.c_int, [_P, _c.POINTER(_I64), _c.POINTER(_c.c_int32), _c.POINTER(_I64), _c.POINTER(_I64)]),
+    "gm2_genbank_copy": (_c.c_int, [_P, _P, _P, _P, _P, _P]),
+    "gm2_genbank_free": (_c.c_int, [_P]),
 }
 
 _lib = None
@@ -154,6 +158,37 @@ def tokenize_npy(path: str, names) -> Optional[tuple]:
     if rc != OK:
         return None               # unsupported or corrupt: NumPy's loader decides (and raises its own errors)
     return ids[:int(off[-1])].copy(), off, counts
+
+
+def scan_genbank(path: str) -> Optional[tuple]:
+    """GenBank file -> (seq uint8[G], names list[str] (F), starts int64[F], ends int64[F], n_features)
+    through gm2_genbank_parse, or None when the file is outside the subset the native scanner handles
+    (the caller then uses `genbank.read_genbank`, which also owns every error message).  Host only;
+    raises what `open` raises for a missing / unreadable file."""
+    text = np.fromfile(path, dtype=np.uint8)
+    lib = load()
+    h = _P()
+    rc = lib.gm2_genbank_parse(_ptr(text) if text.size else None, int(text.size), ctypes.byref(h))
+    if rc != OK:
+        return None
+    try:
+        G, F, nb, nf = _I64(), _c.c_int32(), _I64(), _I64()
+        rc = lib.gm2_genbank_sizes(h, ctypes.byref(G), ctypes.byref(F), ctypes.byref(nb), ctypes.byref(nf))
+        if rc != OK:
+            raise Gm2Error(rc, (lib.gm2_last_error(None) or b"").decode())
+        seq = np.empty(G.value, dtype=np.uint8)
+        starts = np.empty(F.value, dtype=np.int64)
+        ends = np.empty(F.value, dtype=np.int64)
+        name_off = np.empty(F.value + 1, dtype=np.int64)
+        blob = np.empty(max(nb.value, 1), dtype=np.uint8)
+        rc = lib.gm2_genbank_copy(h, _ptr(seq), _ptr(starts), _ptr(ends), _ptr(name_off), _ptr(blob))
+        if rc != OK:
+            raise Gm2Error(rc, (lib.gm2_last_error(None) or b"").decode())
+    finally:
+        lib.gm2_genbank_free(h)
+    raw = blob.tobytes()
+    names = [raw[int(name_off[g]):int(name_off[g + 1])].decode("ascii") for g in range(F.value)]
+    return seq, names, starts, ends, int(nf.value)
 
 
 class PinnedBuffer:

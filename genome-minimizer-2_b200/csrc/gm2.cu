@@ -28,6 +28,7 @@
 
 #include "gm2.h"
 #include "host_tokenize.hpp"
+#include "host_genbank.hpp"
 #include "host_expand.hpp"
 
 #define GM2_API extern "C" __attribute__((visibility("default")))
@@ -1151,6 +1152,53 @@ GM2_API int gm2_tokenize_pickle(const uint8_t* body, int64_t nbytes, int64_t S, 
     } catch (const std::bad_alloc&) {
         return fail(nullptr, GM2_ERR_NOMEM, "gm2_tokenize_pickle: out of host memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-only: GenBank flat file -> sequence + gene table (see host_genbank.hpp)
+// ------------------------------------------------------------------------------------------
+struct gm2_genbank { gm2gb::Genes g; };
+
+GM2_API int gm2_genbank_parse(const uint8_t* text, int64_t nbytes, gm2_genbank** out) {
+    if (!out) return fail(nullptr, GM2_ERR_INVALID, "gm2_genbank_parse: out is NULL");
+    *out = nullptr;
+    if (nbytes < 0 || (nbytes > 0 && !text)) return fail(nullptr, GM2_ERR_INVALID, "gm2_genbank_parse: bad argument");
+    try {
+        gm2_genbank* h = new gm2_genbank();
+        if (gm2gb::scan(std::string_view(reinterpret_cast<const char*>(text), (size_t)nbytes), h->g) != gm2gb::Status::ok) {
+            const std::string why = "gm2_genbank_parse: " + h->g.why;
+            delete h;
+            return fail(nullptr, GM2_ERR_UNSUPPORTED, why);
+        }
+        *out = h;
+        return GM2_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(nullptr, GM2_ERR_NOMEM, "gm2_genbank_parse: out of host memory");
+    }
+}
+GM2_API int gm2_genbank_sizes(const gm2_genbank* h, int64_t* G, int32_t* F, int64_t* name_bytes, int64_t* n_features) {
+    if (!h) return fail(nullptr, GM2_ERR_INVALID, "gm2_genbank_sizes: handle is NULL");
+    if (h->g.start.size() > (size_t)0x7fffffff) return fail(nullptr, GM2_ERR_INVALID, "gm2_genbank_sizes: too many gene features");
+    if (G) *G = (int64_t)h->g.seq.size();
+    if (F) *F = (int32_t)h->g.start.size();
+    if (name_bytes) *name_bytes = (int64_t)h->g.names.size();
+    if (n_features) *n_features = h->g.n_features;
+    return GM2_OK;
+}
+GM2_API int gm2_genbank_copy(const gm2_genbank* h, uint8_t* seq, int64_t* gene_start, int64_t* gene_end,
+                             int64_t* name_off, uint8_t* names) {
+    if (!h) return fail(nullptr, GM2_ERR_INVALID, "gm2_genbank_copy: handle is NULL");
+    const gm2gb::Genes& g = h->g;
+    if (seq && !g.seq.empty()) memcpy(seq, g.seq.data(), g.seq.size());
+    if (gene_start && !g.start.empty()) memcpy(gene_start, g.start.data(), g.start.size() * 8);
+    if (gene_end && !g.end.empty()) memcpy(gene_end, g.end.data(), g.end.size() * 8);
+    if (name_off) memcpy(name_off, g.name_off.data(), g.name_off.size() * 8);
+    if (names && !g.names.empty()) memcpy(names, g.names.data(), g.names.size());
+    return GM2_OK;
+}
+GM2_API int gm2_genbank_free(gm2_genbank* h) {
+    delete h;
+    return GM2_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -15,10 +15,13 @@ from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence,
 import numpy as np
 
 from . import _native
-from .genbank import sequence_bytes
+from .genbank import read_genbank, sequence_bytes
 
 DEFAULT_CHUNK_BYTES = int(os.environ.get("GM2_CHUNK_BYTES", 256 << 20))
 SEQ_ID_PREFIX = "Minimized_E_coli_K12_MG1655_"      # the reference's literal (minimizer_2.py:476, :537)
+
+
+_COORD_MAX = (1 << 62)
 
 
 class GeneTable:
@@ -59,8 +62,10 @@ class GeneTable:
             if feat.type == "gene":
                 names.append(feat.qualifiers.get("gene", [""])[0])
                 # AttributeError on a None location, as in the reference (minimizer_2.py:78)
-                starts.append(int(feat.location.start))
-                ends.append(int(feat.location.end))
+                # (coordinates beyond the genome never meet a base, :94-96; gm2_set_reference clamps to
+                # G, so anything past int64 is clamped here first)
+                starts.append(min(int(feat.location.start), _COORD_MAX))
+                ends.append(min(int(feat.location.end), _COORD_MAX))
                 feats.append(feat)
         return cls(names, np.asarray(starts, dtype=np.int64), np.asarray(ends, dtype=np.int64), feats)
 
@@ -109,6 +114,31 @@ class GeneTable:
         padded = np.zeros((S, fw * 32), dtype=np.uint8)
         padded[:, :F] = keep
         return np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(S, fw)
+
+
+class ReferenceGenome:
+    """What the batch entry functions need of the GenBank record: `record.seq` as bytes and the gene
+    table (minimizer_2.py:455, :35, :59-61, :78-79).  `from_file` reads the file with the native scanner
+    (gm2_genbank_parse, csrc/host_genbank.hpp) and, for anything outside that scanner's plain subset,
+    with `genbank.read_genbank` — same table either way, and the general reader raises the errors."""
+
+    def __init__(self, seq: np.ndarray, table: GeneTable, native: bool = False):
+        self.seq = np.ascontiguousarray(seq, dtype=np.uint8)       # len(ref.seq) == len(record.seq)
+        self.table = table
+        self.native = native                                       # which reader produced it (tests, timing)
+
+    @classmethod
+    def from_record(cls, record) -> "ReferenceGenome":
+        return cls(sequence_bytes(record), GeneTable.from_record(record))
+
+    @classmethod
+    def from_file(cls, genome_path: str) -> "ReferenceGenome":
+        path = os.fspath(genome_path)
+        got = _native.scan_genbank(path)
+        if got is None:
+            return cls.from_record(read_genbank(path))
+        seq, names, starts, ends, _ = got
+        return cls(seq, GeneTable(names, starts, ends), native=True)
 
 
 class _Sized:
@@ -170,7 +200,9 @@ class MinimizerEngine:
 
     def __init__(self, record=None, *, seq: Optional[np.ndarray] = None, table: Optional[GeneTable] = None,
                  device: Optional[int] = None, config: Optional[Dict[int, int]] = None):
-        if record is not None:
+        if isinstance(record, ReferenceGenome):
+            seq, table = record.seq, record.table
+        elif record is not None:
             seq = sequence_bytes(record)
             table = GeneTable.from_record(record)
         if seq is None or table is None:

@@ -174,8 +174,8 @@ def process_multiple_genomes_single_file(genome_path: str, genes_path: str, mode
     if not output_file:
         output_file = os.path.join(_default_dir(), f"minimized_genomes_{model_name}.fasta")
     os.makedirs(os.path.dirname(output_file), exist_ok=True)
-    record = read_genbank(os.fspath(genome_path))                      # reference :455
-    all_lists = _engine.load_gene_lists(genes_path, _engine.GeneTable.from_record(record))   # reference :456
+    record = _engine.ReferenceGenome.from_file(genome_path)            # reference :455
+    all_lists = _engine.load_gene_lists(genes_path, record.table)       # reference :456
     return _engine.run_single_file(record, all_lists, model_name, output_file)
 
 
@@ -186,6 +186,6 @@ def process_multiple_genomes_multiple_files(genome_path: str, genes_path: str, m
     if output_dir is None:
         output_dir = _default_dir()
     os.makedirs(output_dir, exist_ok=True)
-    record = read_genbank(os.fspath(genome_path))                      # reference :515
-    all_lists = _engine.load_gene_lists(genes_path, _engine.GeneTable.from_record(record))   # reference :518
+    record = _engine.ReferenceGenome.from_file(genome_path)            # reference :515
+    all_lists = _engine.load_gene_lists(genes_path, record.table)       # reference :518
     return _engine.run_multi_file(record, all_lists, model_name, output_dir, filename_template)

@@ -228,6 +228,29 @@ int gm2_tokenize_pickle(const uint8_t* body, int64_t nbytes, int64_t S, int64_t 
                         const char* names, const int64_t* name_off, int32_t V,
                         int32_t* ids_out, int64_t ids_cap, int64_t* off_out, int64_t* count_out);
 
+/* Host only (no context, no GPU).  GenBank flat file -> what gm2_set_reference and the name map are
+ * fed with, replacing `SeqIO.read(genome_path, "genbank")` (minimizer_2.py:455, :515; Biopython 1.85,
+ * a third-party dependency of the reference) plus the feature loop of minimizer_2.py:59-61, :78-79:
+ *   G bytes of sequence  = record.seq (ORIGIN lines from column 11, blanks removed, upper-cased);
+ *   F gene rows, file order, one per feature whose key is exactly "gene":
+ *     gene_start / gene_end = int(location.start) / int(location.end): 0-based half-open span over
+ *       all parts of join()/order(), complement() and fuzzy '<' '>' ignored, "N^M" -> [N, N);
+ *     name = first /gene qualifier value with its quotes removed ("" when there is none),
+ *       names[name_off[g] .. name_off[g+1]).
+ * n_features counts every feature-table entry of any key.
+ * gm2_genbank_parse returns GM2_ERR_UNSUPPORTED (reason: gm2_last_error(NULL)) for anything outside
+ * the plain subset — zero or several LOCUS records, carriage returns, bytes outside printable
+ * ASCII / tab / newline, remote, within-position ("N.M") or malformed locations — and the caller
+ * then uses its general reader (genome_minimizer_2_b200/genbank.py), which owns the error messages.
+ * The handle is immutable after parse; gm2_genbank_copy fills caller arrays sized from
+ * gm2_genbank_sizes (seq G, gene_start F, gene_end F, name_off F+1, names name_bytes; any may be NULL). */
+typedef struct gm2_genbank gm2_genbank;
+int gm2_genbank_parse(const uint8_t* text, int64_t nbytes, gm2_genbank** out);
+int gm2_genbank_sizes(const gm2_genbank* h, int64_t* G, int32_t* F, int64_t* name_bytes, int64_t* n_features);
+int gm2_genbank_copy(const gm2_genbank* h, uint8_t* seq, int64_t* gene_start, int64_t* gene_end,
+                     int64_t* name_off, uint8_t* names);
+int gm2_genbank_free(gm2_genbank* h);
+
 /* Host only.  Decoder of the two-bit wire format gm2_emit_host uses internally (GM2_CFG_WIRE), on
  * caller-supplied data: S records whose kept bases arrive as per-(sample, tile) 2-bit pieces; piece
  * (i, t) starts at 32-bit word (rec_off[i] >> 4) + i * (ntiles + 2) + (tile_off[i][t] >> 4) + t of

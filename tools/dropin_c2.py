@@ -47,6 +47,8 @@ try:
     ph = {}
     t0 = time.perf_counter(); record = genbank.read_genbank(gb); ph["read_genbank"] = time.perf_counter() - t0
     t0 = time.perf_counter(); table = engine.GeneTable.from_record(record); ph["gene_table"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); ref = engine.ReferenceGenome.from_file(gb); ph["reference_genome_native"] = time.perf_counter() - t0
+    assert ref.native and ref.table.names == table.names and np.array_equal(ref.table.starts, table.starts)
     t0 = time.perf_counter(); tok = engine.load_gene_lists(npy, table); ph["load_gene_lists_native"] = time.perf_counter() - t0
     assert isinstance(tok, engine.TokenizedLists)
     t0 = time.perf_counter()
