@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--wire", type=int, default=-1, help="GM2_CFG_WIRE for the e2e leg (0 auto, 1 bytes, 2 two-bit)")
     ap.add_argument("--host-threads", type=int, default=-1, help="GM2_CFG_HOST_THREADS")
     ap.add_argument("--flat-run-bytes", type=int, default=-1, help="GM2_CFG_FLAT_RUN_BYTES (0 never, 1048576 always)")
+    ap.add_argument("--run-table", type=int, default=0, help="GM2_CFG_RUN_TABLE (kept-run table entries per warp)")
+    ap.add_argument("--emit-occupancy", type=int, default=-1, help="GM2_CFG_EMIT_OCCUPANCY (0 auto, 3, 4)")
     ap.add_argument("--emit-debug", type=int, default=0, help="timing experiments only (wrong output)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -377,6 +379,10 @@ def main():
         ctx.configure(_native.CFG_ORDER, args.emit_order)
     if args.flat_run_bytes >= 0:
         ctx.configure(_native.CFG_FLAT_RUN_BYTES, args.flat_run_bytes)
+    if args.run_table:
+        ctx.configure(_native.CFG_RUN_TABLE, args.run_table)
+    if args.emit_occupancy >= 0:
+        ctx.configure(_native.CFG_EMIT_OCCUPANCY, args.emit_occupancy)
     if args.wire >= 0:
         ctx.configure(_native.CFG_WIRE, args.wire)
     if args.host_threads >= 0:
@@ -651,7 +657,8 @@ def main():
                    "output": f"device-resident FASTA image, {image_bytes/1e9:.2f} GB per GPU per step",
                    "l2": "no flush needed: each step writes an image >> 126 MB L2",
                    "sharding": "samples; reference replicated; all-gather of image sizes only",
-                   "tile_bytes": args.tile_bytes or 49152, "kept_bases_per_gpu": kept_bases},
+                   "tile_bytes": args.tile_bytes or 49152, "kept_bases_per_gpu": kept_bases,
+                   "emit_ctas_per_sm": ctx.query(_native.Q_LAST_EMIT_CTAS)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_port_c": cpu_c, "verify": verify, "dropin_c1": dropin,
     }

@@ -73,6 +73,7 @@ struct gm2_ctx {
     int wire = 0;                  // gm2_emit_host transport: 0 auto, 1 bytes, 2 two-bit + host expansion
     int host_threads = 0;          // host expansion threads (0: hardware threads / LOCAL_WORLD_SIZE)
     int flat_run_bytes = 640;      // see emit_runs_flat; measured crossover in profiles/r01_emit_experiments.md
+    int emit_occupancy = 0;        // k_emit CTAs per SM: 0 auto (from the kept fraction, see launch_emit), 3, 4
     HeaderPrefix prefix;
 
     // reference
@@ -116,6 +117,13 @@ struct gm2_ctx {
     int64_t *h_len = nullptr, *h_rec_off = nullptr; int64_t h_cap = 0;
     bool planned = false, host_plan = false;
     int64_t first_idx = 0;
+    // kept fraction (kept bases / (S * G)) of the most recent plan whose total has reached the host; -1 unknown.
+    // Feeds the occupancy choice of k_emit only, never the output.  A plan's image size travels to h_total
+    // asynchronously (ev_total), so gm2_plan_async stays asynchronous.
+    double kept_frac = -1.0;
+    int64_t* h_total = nullptr; cudaEvent_t ev_total = nullptr;
+    bool total_pending = false; int64_t total_S = 0;
+    int last_emit_ctas = 0;            // CTAs per SM the last k_emit launch was configured for
 
     // staging for gm2_emit_host
     uint8_t* d_stage[2] = {nullptr, nullptr}; int64_t stage_cap = 0;
@@ -220,8 +228,10 @@ GM2_API int gm2_create(int device, gm2_ctx** out) {
         cudaEventCreateWithFlags(&c->ev_emit[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
     }
-    if ((e = cudaMalloc((void**)&c->d_scan_ticket, sizeof(unsigned int))) != cudaSuccess) {
-        cuda_fail(nullptr, e, "gm2_create: cudaMalloc"); delete c; return GM2_ERR_CUDA;
+    if ((e = cudaMalloc((void**)&c->d_scan_ticket, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&c->h_total, 8)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming)) != cudaSuccess) {
+        cuda_fail(nullptr, e, "gm2_create: cudaMalloc"); gm2_destroy(c); return GM2_ERR_CUDA;
     }
     *out = c;
     return GM2_OK;
@@ -238,6 +248,8 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     for (void* p : frees) if (p) cudaFree(p);
     if (c->h_len) cudaFreeHost(c->h_len);
     if (c->h_rec_off) cudaFreeHost(c->h_rec_off);
+    if (c->h_total) cudaFreeHost(c->h_total);
+    if (c->ev_total) cudaEventDestroy(c->ev_total);
     delete c->pool;
     for (int i = 0; i < 2; ++i) {
         if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
@@ -287,6 +299,9 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     case GM2_CFG_HOST_THREADS:
         if (value < 0 || value > 256) return fail(c, GM2_ERR_INVALID, "host threads must be in 0..256");
         c->host_threads = (int)value; return GM2_OK;
+    case GM2_CFG_EMIT_OCCUPANCY:
+        if (value != 0 && value != 3 && value != 4) return fail(c, GM2_ERR_INVALID, "emit occupancy must be 0 (auto), 3 or 4");
+        c->emit_occupancy = (int)value; return GM2_OK;
     case GM2_CFG_DEBUG:
         c->debug = (int)value; return GM2_OK;
     case GM2_CFG_RUN_TABLE:
@@ -309,6 +324,7 @@ GM2_API int gm2_query(const gm2_ctx* c, int key, int64_t* out) {
     case GM2_Q_KEEP_WORDS:   *out = c->FW; return GM2_OK;
     case GM2_Q_LAST_WIRE:    *out = c->last_wire; return GM2_OK;
     case GM2_Q_LAST_D2H_BYTES: *out = c->last_d2h_bytes; return GM2_OK;
+    case GM2_Q_LAST_EMIT_CTAS: *out = c->last_emit_ctas; return GM2_OK;
     default: return GM2_ERR_INVALID;
     }
 }
@@ -456,6 +472,7 @@ try {
         if (c->packing_req == 2) c->packing = 2;
     }
     c->have_ref = true; c->planned = false; c->host_plan = false; c->mode = 0; c->S = 0;
+    c->kept_frac = -1.0; c->total_pending = false;       // a new genome: no history for the occupancy choice
     return GM2_OK;
 } GM2_CATCH(c, "gm2_set_reference")
 
@@ -653,8 +670,27 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         k_scan_records<<<(unsigned)ntile, SCAN_THREADS, 0, c->stream>>>(c->d_rec_size, c->d_rec_off, S, c->d_scan_desc, c->d_scan_ticket);
         LAUNCH_CHECK(c, "k_scan_records");
     }
+    // the image size follows the plan to the host without a synchronisation (see set_kept_frac)
+    CU(c, cudaMemcpyAsync(c->h_total, c->d_rec_off + S, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(c->ev_total, c->stream));
+    c->total_pending = true; c->total_S = S;
     c->planned = true;
     return GM2_OK;
+}
+
+// kept bases / (S * G) from an image size: records are '>' prefix digits '\n' bases '\n'; the digit
+// count is taken as 6 — the fraction only steers an occupancy choice.
+static void set_kept_frac(gm2_ctx* c, int64_t image_bytes, int64_t S) {
+    if (S <= 0 || c->G <= 0) return;
+    const double framing = (double)S * (double)(c->prefix.len + 8);
+    const double kept = std::max(0.0, (double)image_bytes - framing);
+    c->kept_frac = std::min(1.0, kept / ((double)S * (double)c->G));
+}
+static void poll_kept_frac(gm2_ctx* c) {
+    if (c->total_pending && cudaEventQuery(c->ev_total) == cudaSuccess) {
+        c->total_pending = false;
+        set_kept_frac(c, *c->h_total, c->total_S);
+    }
 }
 
 static int pull_plan(gm2_ctx* c) try {
@@ -673,6 +709,8 @@ static int pull_plan(gm2_ctx* c) try {
     CU(c, cudaMemcpyAsync(c->h_rec_off, c->d_rec_off, (size_t)(S + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->host_plan = true;
+    c->total_pending = false;
+    set_kept_frac(c, c->h_rec_off[S] - c->h_rec_off[0], S);
     return GM2_OK;
 } GM2_CATCH(c, "pull_plan")
 
@@ -741,14 +779,30 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     p.segkept = c->d_segkept; p.tile_off = c->d_tile_off; p.lengths = c->d_len; p.rec_off = c->d_rec_off;
     p.out = dev_out; p.s0 = s0; p.s1 = s1; p.first_idx = c->first_idx;
     p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW; p.batch = (int)batch; p.nbatch = (int)nbatch;
-    p.rt_cap = c->rt_cap;
     p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
     p.prefix = c->prefix; p.debug = c->debug; p.order = c->order; p.flat_run_bytes = c->flat_run_bytes;
-    const size_t sm = 32 + (size_t)p.tile_smem_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 24;
+    // Shared memory and registers decide how many CTAs an SM holds: up to 56 KB and the 62-register
+    // build -> 4 CTAs (32 warps), else the 72-register build -> 3 CTAs.  Measured on the K-12 shape
+    // (profiles/r01_emit_experiments.md, "Occupancy vs retention"): where the kernel is
+    // instruction/latency-bound (short runs, low retention) 4 CTAs are 7-12 % faster; where it is
+    // write-bound (kept fraction above ~0.45) the extra concurrent write streams cost 2-3 %.  With the
+    // default 48 KB tile the only difference between the two is the per-warp run table (32 instead
+    // of 64 entries), so the choice is made here, per launch, from the kept fraction of the latest
+    // plan known to the host — same plan, same bytes either way.
+    auto smem_for = [&](int rt) {
+        return 32 + (size_t)p.tile_smem_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (rt + 2) * 24;
+    };
+    const size_t dense_limit = 56 * 1024;
+    poll_kept_frac(c);
+    int rt_cap = c->rt_cap;
+    const bool want4 = c->emit_occupancy == 4 ||
+                       (c->emit_occupancy == 0 && c->kept_frac >= 0.0 && c->kept_frac < 0.43);
+    if (want4 && smem_for(rt_cap) > dense_limit && smem_for(32) <= dense_limit) rt_cap = 32;
+    p.rt_cap = rt_cap;
+    const size_t sm = smem_for(rt_cap);
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
-    // register budget follows the shared-memory footprint: small tiles -> 4+ CTAs/SM (64 regs),
-    // large tiles -> 3 CTAs/SM (up to 85 regs)
-    const bool dense = sm <= 56 * 1024;
+    const bool dense = sm <= dense_limit;
+    c->last_emit_ctas = dense ? 4 : 3;
     void (*kern)(const EmitParams);
     if (two_bit)
         kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 2> : k_emit<1, 3, 2>) : (dense ? k_emit<0, 4, 2> : k_emit<0, 3, 2>);

@@ -62,6 +62,8 @@ extern "C" {
                                     LOCAL_WORLD_SIZE says several processes share the host), 1 image bytes over PCIe,
                                     2 two bits per base over PCIe + expansion by host threads (error if not ACGT-only) */
 #define GM2_CFG_HOST_THREADS  11 /* host threads for that expansion; 0 = hardware threads / LOCAL_WORLD_SIZE */
+#define GM2_CFG_EMIT_OCCUPANCY 12 /* k_emit CTAs per SM: 0 auto (4 when the latest plan kept less than ~43 % of the bases —
+                                   * short kept runs, instruction-bound — else 3), 3, or 4 (when the shared memory fits) */
 #define GM2_CFG_DEBUG         7  /* timing knock-outs (WRONG output); only effective in -DGM2_EMIT_DEBUG builds */
 
 /* gm2_query keys */
@@ -74,6 +76,7 @@ extern "C" {
 #define GM2_Q_KEEP_WORDS      7  /* 32-bit words per keep row = ceil(F/32)  */
 #define GM2_Q_LAST_WIRE       8  /* wire format the last gm2_emit_host used (1 or 2) */
 #define GM2_Q_LAST_D2H_BYTES  9  /* device->host bytes the last gm2_emit_host moved  */
+#define GM2_Q_LAST_EMIT_CTAS  10 /* CTAs per SM the last k_emit launch was configured for (3 or 4) */
 
 typedef struct gm2_ctx gm2_ctx;
 

@@ -542,6 +542,7 @@ def test_fuzz_kernel_configurations():
             _native.CFG_ORDER: int(rng.choice([0, 1])),
             _native.CFG_EMIT_BATCH: int(rng.choice([0, 1, 3, 16])),
             _native.CFG_FLAT_RUN_BYTES: int(rng.choice([0, 64, 640, 1 << 20])),
+            _native.CFG_EMIT_OCCUPANCY: int(rng.choice([0, 3, 4])),
         }
         with _native.Context(0) as ctx:
             for k, v in cfg.items():
@@ -551,6 +552,33 @@ def test_fuzz_kernel_configurations():
             ctx.plan(first)
             assert np.array_equal(ctx.lengths(), exp_len), (trial, cfg)
             assert np.array_equal(_gpu_image(ctx, S), exp_img), (trial, G, F, S, cfg)
+
+
+def test_emit_occupancy_follows_the_kept_fraction_and_never_changes_the_bytes():
+    """GM2_CFG_EMIT_OCCUPANCY: auto picks the 4-CTA launch form when the plan kept little of the genome
+    and the 3-CTA form otherwise (default 48 KB tile); forcing either gives the same image."""
+    g = synth.make_genome(300_000, 280, seed=61)
+    starts, ends = g.starts_ends()
+    rng = np.random.default_rng(61)
+    S = 24
+    for p_keep, want in ((0.05, 4), (0.95, 3)):
+        rows = synth.pack_keep_rows(rng.random((S, len(starts))) < p_keep)
+        exp_len, _, exp_img = _oracle_image(g.seq, starts, ends, rows, first_idx=0)
+        images = {}
+        for occ in (0, 3, 4):
+            with _native.Context(0) as ctx:
+                ctx.configure(_native.CFG_EMIT_OCCUPANCY, occ)
+                ctx.set_reference(g.seq, starts, ends)
+                ctx.load_keep_host(rows)
+                ctx.plan(0)
+                assert np.array_equal(ctx.lengths(), exp_len)
+                images[occ] = _gpu_image(ctx, S)
+                got = ctx.query(_native.Q_LAST_EMIT_CTAS)
+                assert got == (want if occ == 0 else occ), (p_keep, occ, got)
+            assert np.array_equal(images[occ], exp_img), (p_keep, occ)
+    with _native.Context(0) as ctx:
+        with pytest.raises(_native.Gm2Error):
+            ctx.configure(_native.CFG_EMIT_OCCUPANCY, 5)
 
 
 def test_wire_format_selection_and_threads():
