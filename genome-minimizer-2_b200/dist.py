@@ -19,6 +19,46 @@ import torch.distributed as dist
 from . import engine as _engine
 
 
+_OWN_GROUP = False
+
+
+def ensure_process_group() -> None:
+    """Join the job torchrun started (env:// rendezvous: RANK, WORLD_SIZE, MASTER_ADDR/PORT) unless the caller
+    has already initialised a process group.  NCCL when a GPU is visible (device = LOCAL_RANK), gloo otherwise
+    (CPU tests).  A group created here is destroyed at interpreter exit."""
+    global _OWN_GROUP
+    if dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+    _OWN_GROUP = True
+    import atexit
+
+    def _teardown():
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+    atexit.register(_teardown)
+
+
+def launched_ranks() -> int:
+    """How many ranks share this job: the size of an initialised process group, else torchrun's WORLD_SIZE.
+    GM2_SHARD=0 turns the automatic sharding of the entry functions off (every rank then does the whole job,
+    which is what the reference's CLI would do under torchrun)."""
+    if os.environ.get("GM2_SHARD", "1") == "0":
+        return 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    try:
+        return max(int(os.environ.get("WORLD_SIZE", "1")), 1)
+    except ValueError:
+        return 1
+
+
 def _device_for_backend() -> torch.device:
     if dist.get_backend() == "nccl":
         return torch.device("cuda", torch.cuda.current_device())

@@ -19,6 +19,7 @@ are mirrored in `reporting.py` and re-exported here so every public name of the 
 from __future__ import annotations
 
 import os
+import sys
 from typing import Optional
 
 import numpy as np
@@ -169,23 +170,45 @@ class GenomeMinimiser:
                 "positions_removed": len(self.positions_to_remove)}
 
 
+def _ranks() -> int:
+    """> 1 when the process was started by torchrun (WORLD_SIZE) or sits in an initialised process group:
+    the entry functions then shard the samples over the ranks (dist.py) instead of repeating the whole job
+    in every rank.  GM2_SHARD=0 turns that off."""
+    started_by_torchrun = os.environ.get("WORLD_SIZE", "1") not in ("", "1")
+    if not started_by_torchrun and "torch.distributed" not in sys.modules:
+        return 1                 # nothing can have initialised a process group: torch is not imported for this
+    from . import dist as _dist
+    return _dist.launched_ranks()
+
+
 def process_multiple_genomes_single_file(genome_path: str, genes_path: str, model_name: str, output_file: str = None):
-    """All samples into ONE FASTA file; returns {"genome_count", "average_reduction_pct", "average_length_bp"}."""
+    """All samples into ONE FASTA file; returns {"genome_count", "average_reduction_pct", "average_length_bp"}.
+    Under torchrun (one process per GPU) the samples are sharded over the ranks: every rank writes its own
+    contiguous part of the same file, rank 0 prints the progress lines, all ranks return the same dict."""
     if not output_file:
         output_file = os.path.join(_default_dir(), f"minimized_genomes_{model_name}.fasta")
     os.makedirs(os.path.dirname(output_file), exist_ok=True)
     record = _engine.ReferenceGenome.from_file(genome_path)            # reference :455
     all_lists = _engine.load_gene_lists(genes_path, record.table)       # reference :456
+    if _ranks() > 1:
+        from . import dist as _dist
+        _dist.ensure_process_group()
+        return _dist.run_single_file_sharded(record, all_lists, model_name, output_file)
     return _engine.run_single_file(record, all_lists, model_name, output_file)
 
 
 def process_multiple_genomes_multiple_files(genome_path: str, genes_path: str, model_name: str,
                                             output_dir: str = None,
                                             filename_template: str = "minimized_{model}_{idx:04d}.fasta"):
-    """Each sample into its own FASTA file under output_dir; same return dict (all samples averaged)."""
+    """Each sample into its own FASTA file under output_dir; same return dict (all samples averaged).
+    Under torchrun every rank writes the files of its own contiguous shard of the samples."""
     if output_dir is None:
         output_dir = _default_dir()
     os.makedirs(output_dir, exist_ok=True)
     record = _engine.ReferenceGenome.from_file(genome_path)            # reference :515
     all_lists = _engine.load_gene_lists(genes_path, record.table)       # reference :518
+    if _ranks() > 1:
+        from . import dist as _dist
+        _dist.ensure_process_group()
+        return _dist.run_multi_file_sharded(record, all_lists, model_name, output_dir, filename_template)
     return _engine.run_multi_file(record, all_lists, model_name, output_dir, filename_template)

@@ -16,7 +16,6 @@ import re
 import shutil
 import subprocess
 import sys
-import textwrap
 
 import numpy as np
 import pytest
@@ -34,42 +33,6 @@ STUBS = {
     "matplotlib/__init__.py": "def use(*a, **k):\n    pass\n",
     "matplotlib/pyplot.py": "def ioff(*a, **k):\n    pass\n",
     "seaborn/__init__.py": "",
-    # the engine double: MinimizerEngine's plan_lists / drain / ctx.record_offsets / close surface
-    "gm2_cli_double.py": textwrap.dedent('''
-        import numpy as np
-        from oracle import minimizer_oracle as mo            # checker only (tests)
-        from genome_minimizer_2_b200 import engine
-
-        class OracleEngine:
-            def __init__(self, record):
-                assert isinstance(record, engine.ReferenceGenome)
-                self.ref, self.images, self.ctx = record, [], self
-            def plan_lists(self, all_lists, first_idx=0):
-                t = self.ref.table
-                keeps = []
-                if isinstance(all_lists, engine.TokenizedLists):
-                    for i in range(len(all_lists)):
-                        keep = np.zeros(t.F, dtype=bool)
-                        for v in all_lists.ids[all_lists.off[i]:all_lists.off[i + 1]]:
-                            keep[t.id2gene_idx[t.id2gene_off[v]:t.id2gene_off[v + 1]]] = True
-                        keeps.append(keep)
-                else:
-                    keeps = [mo.keep_vector(t.names, needed) for needed in all_lists]
-                seqs = [mo.minimize_numpy(self.ref.seq, t.starts, t.ends, k).tobytes() for k in keeps]
-                self.images = [mo.record_bytes(first_idx + i, s) for i, s in enumerate(seqs)]
-                return np.asarray([len(s) for s in seqs], dtype=np.int64)
-            def record_offsets(self):
-                return np.concatenate([[0], np.cumsum([len(x) for x in self.images])]).astype(np.int64)
-            def drain(self, sink, max_bytes=0):
-                for a in range(0, len(self.images), 3):          # three records per chunk
-                    b = min(a + 3, len(self.images))
-                    sink(a, b, np.frombuffer(b"".join(self.images[a:b]), dtype=np.uint8))
-            def close(self):
-                pass
-
-        def install():
-            engine.MinimizerEngine = OracleEngine
-    '''),
 }
 
 
@@ -95,14 +58,14 @@ def patched_reference(tmp_path_factory):
     target = ref / "src" / "genome_minimizer_2" / "minimizer" / "minimizer_2.py"
     assert target.exists()
     target.write_text(_shim_from_integration_md() +
-                      "\n# test only: no GPU in this container\nimport gm2_cli_double\ngm2_cli_double.install()\n")
+                      "\n# test only: no GPU in this container\nimport engine_double\nengine_double.install()\n")
     return ref, stubs
 
 
-def _run_cli(patched, args, cwd_files):
+def _run_cli(patched, args, cwd_files, launcher=()):
     ref, stubs = patched
-    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(stubs), ROOT]), MPLBACKEND="Agg")
-    return subprocess.run([sys.executable, "main.py", "--mode", "minimizer", *args], cwd=ref, env=env,
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(stubs), ROOT, os.path.join(ROOT, "tests")]), MPLBACKEND="Agg")
+    return subprocess.run([sys.executable, *launcher, "main.py", "--mode", "minimizer", *args], cwd=ref, env=env,
                           capture_output=True, text=True, timeout=600)
 
 
@@ -168,3 +131,34 @@ def test_unmodified_main_py_multi_file(name, patched_reference, tmp_path):
 def test_missing_inputs_are_reported_by_main_py(patched_reference, tmp_path):
     r = _run_cli(patched_reference, ["--genome-path", str(tmp_path / "absent.gb"), "--genes-path", "x.npy"], tmp_path)
     assert r.returncode == 1 and "✗ Genome file not found" in r.stdout
+
+
+def test_unmodified_main_py_under_torchrun_shards_the_samples(patched_reference, tmp_path):
+    """`torchrun --nproc-per-node 2 main.py --mode minimizer ...`: the entry function notices the ranks,
+    joins the job (gloo here, NCCL on GPUs) and every rank writes its own part of the one file."""
+    case = load_golden("hundred_and_one")
+    gb, npy = _inputs(case, tmp_path)
+    out_dir, log_dir = tmp_path / "out", tmp_path / "logs"
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    launcher = ("-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                "--master-port", str(port), "--redirects", "1", "--log-dir", str(log_dir))
+    r = _run_cli(patched_reference, ["--genome-path", gb, "--genes-path", npy, "--single-file",
+                                     "--output-dir", str(out_dir), "--model-name", case["model_name"]], tmp_path,
+                 launcher=launcher)
+    fasta = out_dir / f"minimized_genomes_{case['model_name']}.fasta"
+    assert fasta.exists(), r.stdout[-3000:] + r.stderr[-3000:]
+    assert _strip_ts(fasta.read_text()) == case["single_file"]
+    # per-rank stdout (torchrun --redirects): rank 0 alone prints the entry function's progress lines
+    logs = {}
+    for root, _dirs, files in os.walk(log_dir):
+        if "stdout.log" in files:
+            logs[os.path.basename(root)] = open(os.path.join(root, "stdout.log")).read()
+    assert sorted(logs) == ["0", "1"], sorted(logs)
+    assert logs["0"].count(case["single_stdout"]) == 1
+    assert "genes present" not in logs["1"]
+    for text in logs.values():                                     # both ranks finish main.py's runner
+        assert "✗" not in text and text.count("✓ GENOME MINIMIZATION COMPLETED!") == 1

@@ -122,3 +122,80 @@ def test_two_ranks_multi_file_mode(tmp_path):
     r = [json.load(open(f"{retp}.{k}")) for k in range(2)]
     assert all(x["ret"] == case["multi_return"] for x in r)
     assert r[0]["stdout"].replace(out, "<OUTDIR>") == case["multi_stdout"] and r[1]["stdout"] == ""
+
+
+# ----------------------------------------------------------------------------------------------
+# the entry functions themselves under a torchrun-style environment (WORLD_SIZE / RANK / MASTER_*):
+# they join the job and shard the samples without being told to (minimizer_2._ranks, dist.ensure_process_group)
+# ----------------------------------------------------------------------------------------------
+def _worker_entry(rank, world, port, case_name, mode, target, ret_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import engine_double
+    from genome_minimizer_2_b200 import minimizer_2 as m2
+    engine_double.install()                                   # no GPU here
+    case = load_golden(case_name)
+    work = os.path.join(os.path.dirname(ret_path), f"in{rank}")
+    os.makedirs(work, exist_ok=True)
+    gb, npy = os.path.join(work, "g.gb"), os.path.join(work, "l.npy")
+    with open(gb, "w") as fh:
+        fh.write(case["genbank"])
+    arr = np.empty(len(case["lists"]), dtype=object)
+    for i, l in enumerate(case["lists"]):
+        arr[i] = l
+    np.save(npy, arr, allow_pickle=True)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        if mode == "single":
+            ret = m2.process_multiple_genomes_single_file(gb, npy, case["model_name"], target)
+        else:
+            ret = m2.process_multiple_genomes_multiple_files(gb, npy, case["model_name"], target)
+    assert dist.is_initialized() and dist.get_world_size() == world
+    with open(f"{ret_path}.{rank}", "w") as fh:
+        json.dump({"ret": ret, "stdout": buf.getvalue()}, fh)
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_entry_function_shards_by_itself_single_file(tmp_path):
+    out, retp = str(tmp_path / "o" / "auto.fasta"), str(tmp_path / "ret")
+    mp.spawn(_worker_entry, args=(2, _free_port(), "hundred_and_one", "single", out, retp), nprocs=2, join=True)
+    case = load_golden("hundred_and_one")
+    lines = open(out, "rb").read().decode().split("\n")
+    assert lines[2].startswith("# Generated on: ")
+    lines[2] = "# Generated on: <TS>"
+    assert "\n".join(lines) == case["single_file"]
+    r = [json.load(open(f"{retp}.{k}")) for k in range(2)]
+    assert all(x["ret"] == case["single_return"] for x in r)
+    assert r[0]["stdout"] == case["single_stdout"] and r[1]["stdout"] == ""
+
+
+def test_entry_function_shards_by_itself_multi_file(tmp_path):
+    out, retp = str(tmp_path / "many"), str(tmp_path / "ret")
+    mp.spawn(_worker_entry, args=(3, _free_port(), "rand_small_1", "multi", out, retp), nprocs=3, join=True)
+    case = load_golden("rand_small_1")
+    files = {fn: open(os.path.join(out, fn), "rb").read().decode() for fn in sorted(os.listdir(out))}
+    assert files == case["multi_files"]
+    r = [json.load(open(f"{retp}.{k}")) for k in range(3)]
+    assert all(x["ret"] == case["multi_return"] for x in r)
+    assert r[0]["stdout"].replace(out, "<OUTDIR>") == case["multi_stdout"] and all(x["stdout"] == "" for x in r[1:])
+
+
+def test_gm2_shard_0_keeps_the_whole_job_in_every_rank(monkeypatch):
+    from genome_minimizer_2_b200 import dist as gdist, minimizer_2 as m2
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    assert m2._ranks() == 4 and gdist.launched_ranks() == 4
+    monkeypatch.setenv("GM2_SHARD", "0")
+    assert m2._ranks() == 1
+    monkeypatch.delenv("GM2_SHARD")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    assert m2._ranks() == 1
