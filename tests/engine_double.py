@@ -14,6 +14,7 @@ class OracleEngine:
     def __init__(self, record):
         ref = record if isinstance(record, engine.ReferenceGenome) else engine.ReferenceGenome.from_record(record)
         self.ref, self.images, self.ctx = ref, [], self
+        self.table = ref.table
 
     def plan_lists(self, all_lists, first_idx=0):
         t = self.ref.table
@@ -29,6 +30,13 @@ class OracleEngine:
         seqs = [mo.minimize_numpy(self.ref.seq, t.starts, t.ends, k).tobytes() for k in keeps]
         self.images = [mo.record_bytes(first_idx + i, s) for i, s in enumerate(seqs)]
         return np.asarray([len(s) for s in seqs], dtype=np.int64)
+
+    def minimize_one(self, needed, idx=0):
+        """(indices of the removed genes in file order, minimized sequence) — MinimizerEngine.minimize_one."""
+        t = self.ref.table
+        keep = mo.keep_vector(t.names, needed)
+        seq = mo.minimize_numpy(self.ref.seq, t.starts, t.ends, keep).tobytes().decode("ascii")
+        return np.flatnonzero(~keep), seq
 
     def record_offsets(self):
         return np.concatenate([[0], np.cumsum([len(x) for x in self.images])]).astype(np.int64)
