@@ -97,3 +97,38 @@ def test_one_engine_per_record_object(golden_paths, golden):
     import gc
     gc.collect()
     assert len(m2._ENGINES) == 0                                         # dropped with the record
+
+
+# ---- the two entry functions over every fixture (host logic only: loaders, progress lines, F10 averages, files)
+def test_single_file_entry_host_logic(golden, golden_paths, tmp_path, capsys):
+    gb, npy = golden_paths
+    out = tmp_path / "nested" / "dir" / "out.fasta"                      # parents are created (reference :453)
+    ret = m2.process_multiple_genomes_single_file(gb, npy, golden["model_name"], str(out))
+    stdout = capsys.readouterr().out
+    data = out.read_bytes().decode()
+    lines = data.split("\n")
+    assert lines[2].startswith("# Generated on: ") and len(lines[2]) == len("# Generated on: 2026-01-01T00:00:00")
+    lines[2] = "# Generated on: <TS>"
+    data = "\n".join(lines)
+    if "single_file" in golden:
+        assert data == golden["single_file"]
+    else:
+        assert hashlib.sha256(data.encode()).hexdigest() == golden["single_file_sha256"]
+    assert stdout == golden["single_stdout"]
+    assert ret == golden["single_return"]
+
+
+def test_multi_file_entry_host_logic(golden, golden_paths, tmp_path, capsys):
+    import os
+    from pathlib import Path
+    gb, npy = golden_paths
+    out_dir = tmp_path / "multi"
+    ret = m2.process_multiple_genomes_multiple_files(gb, npy, golden["model_name"], Path(out_dir))   # main.py passes a Path
+    stdout = capsys.readouterr().out
+    files = {fn: (out_dir / fn).read_bytes().decode() for fn in sorted(os.listdir(out_dir))}
+    if "multi_files" in golden:
+        assert files == golden["multi_files"]
+    else:
+        assert {k: hashlib.sha256(v.encode()).hexdigest() for k, v in files.items()} == golden["multi_files_sha256"]
+    assert stdout.replace(str(out_dir), "<OUTDIR>") == golden["multi_stdout"]
+    assert ret == golden["multi_return"]
