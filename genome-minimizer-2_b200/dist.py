@@ -19,14 +19,10 @@ import torch.distributed as dist
 from . import engine as _engine
 
 
-_OWN_GROUP = False
-
-
 def ensure_process_group() -> None:
     """Join the job torchrun started (env:// rendezvous: RANK, WORLD_SIZE, MASTER_ADDR/PORT) unless the caller
     has already initialised a process group.  NCCL when a GPU is visible (device = LOCAL_RANK), gloo otherwise
     (CPU tests).  A group created here is destroyed at interpreter exit."""
-    global _OWN_GROUP
     if dist.is_initialized():
         return
     if torch.cuda.is_available():
@@ -35,7 +31,6 @@ def ensure_process_group() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         dist.init_process_group("gloo")
-    _OWN_GROUP = True
     import atexit
 
     def _teardown():
