@@ -18,8 +18,8 @@ ABI_VERSION = 1
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY, CFG_RUN_TABLE, CFG_DEBUG, CFG_ORDER = 1, 2, 3, 4, 5, 6, 7, 8
-CFG_FLAT_RUN_BYTES, CFG_WIRE, CFG_HOST_THREADS, CFG_EMIT_OCCUPANCY = 9, 10, 11, 12
-Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS, Q_LAST_WIRE, Q_LAST_D2H_BYTES, Q_LAST_EMIT_CTAS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+CFG_FLAT_RUN_BYTES, CFG_WIRE, CFG_HOST_THREADS, CFG_EMIT_OCCUPANCY, CFG_FLAT_MODE = 9, 10, 11, 12, 13
+Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS, Q_LAST_WIRE, Q_LAST_D2H_BYTES, Q_LAST_EMIT_CTAS, Q_LAST_FLAT_MODE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 
 _c = ctypes
 _P = _c.c_void_p
@@ -49,6 +49,7 @@ SIGNATURES = {
     "gm2_plan": (_c.c_int, [_P, _I64]),
     "gm2_plan_async": (_c.c_int, [_P, _I64]),
     "gm2_get_lengths": (_c.c_int, [_P, _P]),
+    "gm2_get_lengths_dev": (_c.c_int, [_P, _P]),
     "gm2_get_record_offsets": (_c.c_int, [_P, _P]),
     "gm2_get_keep_rows": (_c.c_int, [_P, _P]),
     "gm2_image_bytes": (_c.c_int, [_P, _I64, _I64, _c.POINTER(_I64)]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "gm2_diag_fill": (_c.c_int, [_P, _P, _I64, _c.c_uint32]),
     "gm2_diag_fill_streams": (_c.c_int, [_P, _P, _I64, _I64, _c.c_int32, _I64, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32]),
     "gm2_diag_range_hashes": (_c.c_int, [_P, _P, _I64, _P, _I64, _P]),
+    "gm2_diag_host_fill": (_c.c_int, [_P, _I64, _c.c_int32, _c.c_int32, _c.POINTER(_c.c_double)]),
     "gm2_diag_expand": (_c.c_int, [_P, _P, _P, _P, _I64, _c.c_int32, _I64, _c.c_char_p, _P, _c.c_int32, _c.c_int32]),
     "gm2_tokenize_pickle": (_c.c_int, [_P, _I64, _I64, _I64, _P, _P, _c.c_int32, _P, _I64, _P, _P]),
     "gm2_genbank_parse": (_c.c_int, [_P, _I64, _c.POINTER(_P)]),
@@ -222,6 +224,16 @@ class PinnedBuffer:
             pass
 
 
+def host_fill_gbs(buf, threads: int = 0, reps: int = 3) -> float:
+    """Non-temporal fill of a host buffer (numpy uint8 array or PinnedBuffer) by `threads` threads: GB/s."""
+    arr = buf.array if isinstance(buf, PinnedBuffer) else buf
+    out = _c.c_double(0.0)
+    rc = load().gm2_diag_host_fill(_ptr(arr), int(arr.size), int(threads), int(reps), ctypes.byref(out))
+    if rc != OK:
+        raise Gm2Error(rc, (load().gm2_last_error(None) or b"").decode())
+    return float(out.value)
+
+
 class Context:
     """One gm2 context == one GPU.  Thin, typed wrapper; raises Gm2Error on any failure."""
 
@@ -344,6 +356,10 @@ class Context:
         out = np.empty(self.S, dtype=np.int64)
         self._ck(self._lib.gm2_get_lengths(self._h, _ptr(out)))
         return out
+
+    def lengths_dev(self, dev_ptr: int):
+        """Lengths of the current plan copied device-to-device into `dev_ptr` (S int64), asynchronously."""
+        self._ck(self._lib.gm2_get_lengths_dev(self._h, int(dev_ptr)))
 
     def record_offsets(self) -> np.ndarray:
         out = np.empty(self.S + 1, dtype=np.int64)

@@ -72,7 +72,9 @@ struct gm2_ctx {
     int order = 1;
     int wire = 0;                  // gm2_emit_host transport: 0 auto, 1 bytes, 2 two-bit + host expansion
     int host_threads = 0;          // host expansion threads (0: hardware threads / LOCAL_WORLD_SIZE)
-    int flat_run_bytes = 640;      // see emit_runs_flat; measured crossover in profiles/r01_emit_experiments.md
+    int flat_run_bytes = 640;      // visits with a shorter mean kept run take the flat form; crossover measured in profiles/
+    int flat_mode = 0;             // short-run form: 0 auto (from the kept fraction, see launch_emit), 1 emit_runs_flat
+                                   // (cursor per lane, chosen per flushed batch), 2 visit_flat (bitmap-indexed, chosen per visit)
     int emit_occupancy = 0;        // k_emit CTAs per SM: 0 auto (from the kept fraction, see launch_emit), 3, 4
     HeaderPrefix prefix;
 
@@ -111,6 +113,7 @@ struct gm2_ctx {
     int32_t* d_tile_off = nullptr; int64_t tile_off_cap = 0;   // elements
     int64_t *d_len = nullptr, *d_rec_size = nullptr, *d_rec_off = nullptr;
     int64_t len_cap = 0, rec_size_cap = 0, rec_off_cap = 0;
+    int32_t* d_hdr_len = nullptr; int64_t hdr_len_cap = 0;      // bytes of every record's header line (k_plan)
     unsigned long long* d_scan_desc = nullptr; int64_t scan_desc_cap = 0;
     unsigned int* d_scan_ticket = nullptr;
     // plan outputs (pinned host mirror)
@@ -124,6 +127,7 @@ struct gm2_ctx {
     int64_t* h_total = nullptr; cudaEvent_t ev_total = nullptr;
     bool total_pending = false; int64_t total_S = 0;
     int last_emit_ctas = 0;            // CTAs per SM the last k_emit launch was configured for
+    int last_flat_mode = 1;            // short-run form it was built with (1 or 2)
 
     // staging for gm2_emit_host
     uint8_t* d_stage[2] = {nullptr, nullptr}; int64_t stage_cap = 0;
@@ -164,12 +168,17 @@ static int dev_reserve(gm2_ctx* c, T** p, int64_t* cap, int64_t need) {
     *cap = n;
     return GM2_OK;
 }
+// Uploads go through the stream the kernels run on (it is created non-blocking, so nothing orders it
+// behind the legacy default stream) and are complete when the call returns.
 template <typename T>
 static int dev_upload(gm2_ctx* c, T** p, const std::vector<T>& v) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (*p) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(*p); *p = nullptr; }
     size_t n = std::max<size_t>(v.size(), 1);
     CU(c, cudaMalloc((void**)p, n * sizeof(T)));
-    if (!v.empty()) CU(c, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) {
+        CU(c, cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
     return GM2_OK;
 }
 
@@ -243,7 +252,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     cudaDeviceSynchronize();
     void* frees[] = {c->d_seq, c->d_seq2, c->d_tile_slot, c->d_slot_src, c->d_slot_len, c->d_slot_cov, c->d_cov_ovf,
                      c->d_first_gene, c->d_next_same, c->d_forced_ids, c->d_force_keep, c->d_has_gene, c->d_counts, c->own_ids, c->own_ids_off, c->own_keep, c->d_segkept,
-                     c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_scan_desc, c->d_scan_ticket,
+                     c->d_tile_off, c->d_len, c->d_rec_size, c->d_rec_off, c->d_hdr_len, c->d_scan_desc, c->d_scan_ticket,
                      c->d_stage[0], c->d_stage[1]};
     for (void* p : frees) if (p) cudaFree(p);
     if (c->h_len) cudaFreeHost(c->h_len);
@@ -293,6 +302,9 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     case GM2_CFG_FLAT_RUN_BYTES:
         if (value < 0 || value > (1 << 20)) return fail(c, GM2_ERR_INVALID, "flat run bytes must be in 0..1048576");
         c->flat_run_bytes = (int)value; return GM2_OK;
+    case GM2_CFG_FLAT_MODE:
+        if (value < 0 || value > 2) return fail(c, GM2_ERR_INVALID, "flat mode must be 0 (auto), 1 (cursor per lane) or 2 (bitmap-indexed)");
+        c->flat_mode = (int)value; return GM2_OK;
     case GM2_CFG_WIRE:
         if (value < 0 || value > 2) return fail(c, GM2_ERR_INVALID, "wire must be 0 (auto), 1 (bytes) or 2 (two-bit)");
         c->wire = (int)value; return GM2_OK;
@@ -325,6 +337,7 @@ GM2_API int gm2_query(const gm2_ctx* c, int key, int64_t* out) {
     case GM2_Q_LAST_WIRE:    *out = c->last_wire; return GM2_OK;
     case GM2_Q_LAST_D2H_BYTES: *out = c->last_d2h_bytes; return GM2_OK;
     case GM2_Q_LAST_EMIT_CTAS: *out = c->last_emit_ctas; return GM2_OK;
+    case GM2_Q_LAST_FLAT_MODE: *out = c->last_flat_mode; return GM2_OK;
     default: return GM2_ERR_INVALID;
     }
 }
@@ -439,8 +452,9 @@ try {
     if (c->d_seq) { cudaFree(c->d_seq); c->d_seq = nullptr; }
     const size_t seq_alloc = (size_t)ntiles * (size_t)T + 256;
     CU(c, cudaMalloc((void**)&c->d_seq, seq_alloc));
-    CU(c, cudaMemset(c->d_seq, 0, seq_alloc));
-    if (G > 0) CU(c, cudaMemcpy(c->d_seq, seq, (size_t)G, cudaMemcpyHostToDevice));
+    CU(c, cudaMemsetAsync(c->d_seq, 0, seq_alloc, c->stream));
+    if (G > 0) CU(c, cudaMemcpyAsync(c->d_seq, seq, (size_t)G, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     int rc;
     if ((rc = dev_upload(c, &c->d_tile_slot, tile_slot))) return rc;
     if ((rc = dev_upload(c, &c->d_slot_src, slot_src))) return rc;
@@ -624,6 +638,7 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
     if ((rc = dev_reserve(c, &c->d_len, &c->len_cap, S + 1))) return rc;
     if ((rc = dev_reserve(c, &c->d_rec_size, &c->rec_size_cap, S + 1))) return rc;
     if ((rc = dev_reserve(c, &c->d_rec_off, &c->rec_off_cap, S + 1))) return rc;
+    if ((rc = dev_reserve(c, &c->d_hdr_len, &c->hdr_len_cap, S + 1))) return rc;
     const uint32_t* keep = c->keep_in;
     if (c->mode == 3) {
         if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;
@@ -659,7 +674,7 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         const int64_t blocks = (S + PLAN_NS - 1) / PLAN_NS;
         k_plan<<<(unsigned)blocks, 256, sm, c->stream>>>(S, c->FW, keep, c->ntiles, c->d_tile_slot, c->d_slot_len,
                                                          c->d_slot_cov, c->d_cov_ovf, c->SW, c->d_segkept, c->d_tile_off,
-                                                         c->d_len, c->d_rec_size, first_idx, c->prefix.len);
+                                                         c->d_len, c->d_rec_size, c->d_hdr_len, first_idx, c->prefix.len);
         LAUNCH_CHECK(c, "k_plan");
     }
     {
@@ -726,6 +741,14 @@ GM2_API int gm2_get_lengths(gm2_ctx* c, int64_t* out) {
     if (c->S > 0) { if (!out) return fail(c, GM2_ERR_INVALID, "gm2_get_lengths: out is NULL"); memcpy(out, c->h_len, (size_t)c->S * 8); }
     return GM2_OK;
 }
+GM2_API int gm2_get_lengths_dev(gm2_ctx* c, int64_t* dev_out) {
+    if (!c) return GM2_ERR_INVALID;
+    if (!c->planned) return fail(c, GM2_ERR_STATE, "gm2_get_lengths_dev: call gm2_plan / gm2_plan_async first");
+    if (c->S > 0 && !dev_out) return fail(c, GM2_ERR_INVALID, "gm2_get_lengths_dev: dev_lengths is NULL");
+    CU(c, cudaSetDevice(c->device));
+    if (c->S > 0) CU(c, cudaMemcpyAsync(dev_out, c->d_len, (size_t)c->S * 8, cudaMemcpyDeviceToDevice, c->stream));
+    return GM2_OK;
+}
 GM2_API int gm2_get_record_offsets(gm2_ctx* c, int64_t* out) {
     if (!c || !out) return GM2_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
@@ -777,6 +800,7 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     p.seq = two_bit ? c->d_seq2 : c->d_seq; p.tile_smem_bytes = two_bit ? c->tile_bytes / 4 : c->tile_bytes;
     p.tile_slot = c->d_tile_slot; p.slot_src = c->d_slot_src; p.slot_len = c->d_slot_len;
     p.segkept = c->d_segkept; p.tile_off = c->d_tile_off; p.lengths = c->d_len; p.rec_off = c->d_rec_off;
+    p.hdr_len = c->d_hdr_len;
     p.out = dev_out; p.s0 = s0; p.s1 = s1; p.first_idx = c->first_idx;
     p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW; p.batch = (int)batch; p.nbatch = (int)nbatch;
     p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
@@ -799,15 +823,27 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
                        (c->emit_occupancy == 0 && c->kept_frac >= 0.0 && c->kept_frac < 0.43);
     if (want4 && smem_for(rt_cap) > dense_limit && smem_for(32) <= dense_limit) rt_cap = 32;
     p.rt_cap = rt_cap;
+    // visit_flat keeps packed 4-byte entries in the same per-warp region ((rt_cap + 2) * 24 bytes): table A and the
+    // event table with 2 * rt_cap + 2 entries each, the rest (2 * rt_cap + 8 words) is its vector bitmap
+    // Which short-run form (measured, profiles/r02_emit_low_retention.md): the bitmap-indexed whole-visit form wins
+    // where nearly every run is an intergenic gap (gene retention ~10 %: kept fraction of the bases below ~0.26),
+    // the per-batch cursor form from ~20 % up, where long runs inside short-run tiles go to the run-by-run stream.
+    const bool want2 = c->flat_mode == 2 || (c->flat_mode == 0 && c->kept_frac >= 0.0 && c->kept_frac < 0.26);
+    const bool flat2 = want2 && !two_bit && c->tile_bytes <= FLAT_MAX_TILE;
+    p.flat_cap = flat2 ? 2 * rt_cap : 0;
+    p.flat_bm_words = flat2 ? 2 * rt_cap + 8 : 0;
     const size_t sm = smem_for(rt_cap);
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
     const bool dense = sm <= dense_limit;
     c->last_emit_ctas = dense ? 4 : 3;
+    c->last_flat_mode = flat2 ? 2 : 1;
     void (*kern)(const EmitParams);
     if (two_bit)
-        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 2> : k_emit<1, 3, 2>) : (dense ? k_emit<0, 4, 2> : k_emit<0, 3, 2>);
+        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 2, 1> : k_emit<1, 3, 2, 1>) : (dense ? k_emit<0, 4, 2, 1> : k_emit<0, 3, 2, 1>);
+    else if (flat2)
+        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 1, 2> : k_emit<1, 3, 1, 2>) : (dense ? k_emit<0, 4, 1, 2> : k_emit<0, 3, 1, 2>);
     else
-        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 1> : k_emit<1, 3, 1>) : (dense ? k_emit<0, 4, 1> : k_emit<0, 3, 1>);
+        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 1, 1> : k_emit<1, 3, 1, 1>) : (dense ? k_emit<0, 4, 1, 1> : k_emit<0, 3, 1, 1>);
     CU(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     kern<<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
     LAUNCH_CHECK(c, "k_emit");
@@ -915,7 +951,7 @@ static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_ou
         v.packed = c->h_pstage[buf]; v.tile_off = c->h_toff[buf]; v.rec_off = c->h_rec_off; v.lengths = c->h_len;
         v.out = host_out + (c->h_rec_off[chunks[i].first] - c->h_rec_off[s0]);
         v.s0 = chunks[i].first; v.s1 = chunks[i].second; v.first_idx = c->first_idx; v.ntiles = nt;
-        v.prefix = c->prefix.text; v.prefix_len = c->prefix.len; v.simd = true;
+        v.prefix = c->prefix.text; v.prefix_len = c->prefix.len; v.simd = 1;
         c->pool->expand_chunk(v);
         return GM2_OK;
     };
@@ -1256,6 +1292,19 @@ GM2_API int gm2_genbank_free(gm2_genbank* h) {
 }
 
 // ------------------------------------------------------------------------------------------
+// host-only: write ceiling of the expansion's store pattern (bench.py)
+// ------------------------------------------------------------------------------------------
+GM2_API int gm2_diag_host_fill(uint8_t* host, int64_t bytes, int32_t threads, int32_t reps, double* gbs) {
+    if (!host || bytes <= 0 || !gbs) return fail(nullptr, GM2_ERR_INVALID, "gm2_diag_host_fill: bad argument");
+    try {
+        *gbs = gm2host::fill_probe(host, bytes, threads > 0 ? threads : gm2host::default_threads(), reps > 0 ? reps : 1);
+        return GM2_OK;
+    } catch (const std::exception& e) {
+        return fail(nullptr, GM2_ERR_NOMEM, std::string("gm2_diag_host_fill: ") + e.what());
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-only: the decoder of the two-bit wire format on caller-supplied data (tests, probes)
 // ------------------------------------------------------------------------------------------
 GM2_API int gm2_diag_expand(const uint32_t* packed, const int32_t* tile_off, const int64_t* rec_off,
@@ -1269,7 +1318,7 @@ GM2_API int gm2_diag_expand(const uint32_t* packed, const int32_t* tile_off, con
     gm2host::ChunkView v;
     v.packed = packed; v.tile_off = tile_off; v.rec_off = rec_off; v.lengths = lengths; v.out = out;
     v.s0 = 0; v.s1 = S; v.first_idx = first_idx; v.ntiles = ntiles;
-    v.prefix = full.c_str(); v.prefix_len = (int)full.size(); v.simd = simd != 0;
+    v.prefix = full.c_str(); v.prefix_len = (int)full.size(); v.simd = simd;
     gm2host::expand_chunk(v, threads > 0 ? threads : gm2host::default_threads());
     return GM2_OK;
 }

@@ -11,8 +11,10 @@
 #include "host_expand.hpp"
 
 #include <immintrin.h>
+#include <sched.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <cstdlib>
@@ -62,14 +64,61 @@ static void expand_avx2_aligned(uint8_t* dst, const uint8_t* p, int64_t b0, int6
     _mm_sfence();                                          // this thread's non-temporal stores ordered before it signals completion
 }
 
+// AVX-512 VBMI: 64 bases (128 bits of the stream) -> one whole 64-byte cache line per step, one
+// non-temporal store each (a full line leaves the core in one piece; two 32-byte halves may not).
+// vpermb puts stream bytes 2k, 2k+1, 2k+2 at the bottom of qword k, vpmultishiftqb takes from each
+// qword the 8 fields starting at bit (phase + 2 i) — the bit phase of the stream costs nothing —
+// and vpshufb maps the two low bits of every byte to its letter.  Reads 32 bytes per step from the
+// group's first stream byte (16 used): the caller leaves the last group to the scalar tail.
+__attribute__((target("avx512f,avx512bw,avx512vbmi")))
+static void expand_avx512_aligned(uint8_t* dst, const uint8_t* p, int64_t b0, int64_t ngroups) {
+    alignas(64) uint8_t idx_b[64], ctl_b[64], lut_b[64];
+    const int sh = 2 * (int)(b0 & 3);
+    for (int k = 0; k < 8; ++k)
+        for (int i = 0; i < 8; ++i) {
+            idx_b[8 * k + i] = (uint8_t)(2 * k + (i < 3 ? i : 0));
+            ctl_b[8 * k + i] = (uint8_t)(sh + 2 * i);
+        }
+    for (int i = 0; i < 64; ++i) lut_b[i] = (uint8_t)ACGT[i & 3];
+    const __m512i idx = _mm512_load_si512(idx_b), ctl = _mm512_load_si512(ctl_b), lut = _mm512_load_si512(lut_b);
+    const __m512i m3 = _mm512_set1_epi8(3);
+    const uint8_t* q = p + (b0 >> 2);
+    for (int64_t g = 0; g < ngroups; ++g, q += 16, dst += 64) {
+        const __m512i src = _mm512_castsi256_si512(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(q)));
+        const __m512i rep = _mm512_permutexvar_epi8(idx, src);
+        const __m512i code = _mm512_and_si512(_mm512_multishift_epi64_epi8(ctl, rep), m3);
+        _mm512_stream_si512(reinterpret_cast<__m512i*>(dst), _mm512_shuffle_epi8(lut, code));
+    }
+    _mm_sfence();
+}
+
 static bool have_avx2() {
     static const bool v = __builtin_cpu_supports("avx2");
     return v;
 }
+static bool have_avx512() {
+    static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                          __builtin_cpu_supports("avx512vbmi");
+    return v;
+}
 
-void expand_bases(uint8_t* dst, const uint32_t* words, int64_t nbases, bool allow_simd) {
+int simd_level() { return have_avx512() ? 3 : have_avx2() ? 2 : 0; }
+
+void expand_bases(uint8_t* dst, const uint32_t* words, int64_t nbases, int simd) {
     const uint8_t* p = reinterpret_cast<const uint8_t*>(words);
-    if (!allow_simd || !have_avx2() || nbases < 96) { expand_scalar(dst, p, 0, nbases); return; }
+    if (simd == 1) simd = simd_level();
+    if (simd == 3 && !have_avx512()) simd = 2;
+    if (simd == 2 && !have_avx2()) simd = 0;
+    if (simd == 3 && nbases >= 256) {
+        const int64_t head = (int64_t)((64 - ((uintptr_t)dst & 63)) & 63);
+        expand_scalar(dst, p, 0, head);
+        const int64_t groups = (nbases - head) / 64 - 1;            // the last whole group is the scalar tail's (over-read)
+        expand_avx512_aligned(dst + head, p, head, groups);
+        const int64_t done = head + 64 * groups;
+        expand_scalar(dst + done, p, done, nbases - done);
+        return;
+    }
+    if (simd < 2 || nbases < 96) { expand_scalar(dst, p, 0, nbases); return; }
     int64_t head = (int64_t)((32 - ((uintptr_t)dst & 31)) & 31);
     expand_scalar(dst, p, 0, head);
     const int64_t groups = (nbases - head) / 32;
@@ -148,8 +197,39 @@ struct Pool::Impl {
     }
 };
 
+// CPUs this process may use, cut into LOCAL_WORLD_SIZE equal slices; this rank's slice (LOCAL_RANK).
+// Workers are pinned round-robin inside it (GM2_HOST_PIN=0: leave them to the scheduler): ranks that
+// share a host then do not migrate onto each other's cores in the middle of a chunk.
+static std::vector<int> my_cpus() {
+    std::vector<int> all;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) all.push_back(c);
+    const int R = local_ranks();
+    int r = 0;
+    if (const char* e = getenv("LOCAL_RANK")) r = atoi(e);
+    if (R <= 1 || r < 0 || r >= R || (int)all.size() < R) return all;
+    const size_t a = all.size() * (size_t)r / (size_t)R, b = all.size() * (size_t)(r + 1) / (size_t)R;
+    return std::vector<int>(all.begin() + (long)a, all.begin() + (long)b);
+}
+
+static bool pin_enabled() {
+    const char* e = getenv("GM2_HOST_PIN");
+    return !(e && e[0] == '0');
+}
+
 Pool::Pool(int threads) : impl_(new Impl), threads_(threads < 1 ? 1 : threads) {
-    for (int t = 1; t < threads_; ++t) impl_->workers.emplace_back([this] { impl_->worker(); });
+    const std::vector<int> cpus = pin_enabled() ? my_cpus() : std::vector<int>();
+    for (int t = 1; t < threads_; ++t) {
+        impl_->workers.emplace_back([this] { impl_->worker(); });
+        if (!cpus.empty()) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[(size_t)t % cpus.size()], &one);
+            pthread_setaffinity_np(impl_->workers.back().native_handle(), sizeof(one), &one);   // best effort
+        }
+    }
 }
 
 Pool::~Pool() {
@@ -190,12 +270,75 @@ int local_ranks() {
 }
 
 int default_threads() {
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 1;
-    int t = (int)hw / local_ranks();
+    if (const char* e = getenv("GM2_HOST_THREADS")) { const int t = atoi(e); if (t > 0) return t > 256 ? 256 : t; }
+    // the CPUs this process is allowed on (cgroup / taskset aware), shared equally among the local ranks
+    int n = 0;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    if (n <= 0) n = 1;
+    int t = n / local_ranks();
     if (t < 1) t = 1;
-    if (t > 32) t = 32;
+    if (t > 64) t = 64;
     return t;
+}
+
+// ---- host write ceiling: the expansion's store pattern without the decode ------------------------
+__attribute__((target("avx2")))
+static void fill_nt(uint8_t* dst, int64_t n) {
+    const __m256i v = _mm256_set1_epi8('A');
+    int64_t i = 0;
+    for (; i < n && ((uintptr_t)(dst + i) & 31); ++i) dst[i] = 'A';
+    for (; i + 32 <= n; i += 32) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), v);
+    for (; i < n; ++i) dst[i] = 'A';
+    _mm_sfence();
+}
+__attribute__((target("avx512f")))
+static void fill_nt512(uint8_t* dst, int64_t n) {
+    const __m512i v = _mm512_set1_epi8('A');
+    int64_t i = 0;
+    for (; i < n && ((uintptr_t)(dst + i) & 63); ++i) dst[i] = 'A';
+    for (; i + 64 <= n; i += 64) _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + i), v);
+    for (; i < n; ++i) dst[i] = 'A';
+    _mm_sfence();
+}
+
+double fill_probe(uint8_t* host, int64_t bytes, int threads, int reps) {
+    if (threads < 1) threads = 1;
+    const std::vector<int> cpus = pin_enabled() ? my_cpus() : std::vector<int>();
+    const int64_t piece = (int64_t)4 << 20;                      // tasks of 4 MiB from a shared counter, as the expansion takes tasks
+    const int64_t ntask = (bytes + piece - 1) / piece;
+    double best = 0.0;
+    for (int rep = 0; rep < reps; ++rep) {
+        std::atomic<int64_t> next{0};
+        auto work = [&] {
+            for (;;) {
+                const int64_t t = next.fetch_add(1, std::memory_order_relaxed);
+                if (t >= ntask) break;
+                const int64_t a = t * piece, n = std::min(piece, bytes - a);
+                if (have_avx512()) fill_nt512(host + a, n);
+                else if (have_avx2()) fill_nt(host + a, n);
+                else memset(host + a, 'A', (size_t)n);
+            }
+        };
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; ++t) {
+            th.emplace_back(work);
+            if (!cpus.empty()) {
+                cpu_set_t one;
+                CPU_ZERO(&one);
+                CPU_SET(cpus[(size_t)t % cpus.size()], &one);
+                pthread_setaffinity_np(th.back().native_handle(), sizeof(one), &one);
+            }
+        }
+        work();
+        for (auto& x : th) x.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt > 0) best = std::max(best, (double)bytes / dt / 1e9);
+    }
+    return best;
 }
 
 }  // namespace gm2host

@@ -23,12 +23,14 @@ struct ChunkView {
     int ntiles;
     const char* prefix;      // '>' + id prefix (no terminator needed)
     int prefix_len;
-    bool simd;               // allow the AVX2 path (off: portable scalar decoder, used by tests)
+    int simd;                // decoder: 0 portable scalar (tests), 1 best the CPU has, 2 AVX2, 3 AVX-512 VBMI
 };
 
 // nbases bases starting at bit 0 of words[0] -> ASCII at dst (any alignment).  May read up to 16 bytes
 // past the last word that holds a base.
-void expand_bases(uint8_t* dst, const uint32_t* words, int64_t nbases, bool allow_simd);
+void expand_bases(uint8_t* dst, const uint32_t* words, int64_t nbases, int simd);
+// decoder the CPU supports: 0 scalar, 2 AVX2, 3 AVX-512 VBMI
+int simd_level();
 
 // Headers, sequences and trailing newlines of every record of the chunk, decoded by `threads` threads
 // (the caller's included) that take part-of-a-sample tasks from a shared counter.  A Pool keeps its
@@ -50,7 +52,9 @@ void expand_chunk(const ChunkView& v, int threads);
 
 // processes sharing this host (LOCAL_WORLD_SIZE, as torchrun sets it; 1 when absent)
 int local_ranks();
-// hardware threads / local_ranks(), clamped to [1, 32]
+// GM2_HOST_THREADS, else the CPUs this process may run on / local_ranks(), clamped to [1, 64]
 int default_threads();
+// `threads` threads fill `host` with non-temporal stores (4 MiB tasks from a shared counter): best GB/s of `reps` passes
+double fill_probe(uint8_t* host, int64_t bytes, int threads, int reps);
 
 }  // namespace gm2host

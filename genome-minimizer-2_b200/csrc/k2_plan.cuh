@@ -25,7 +25,7 @@ k_plan(int64_t S, int FW, const uint32_t* __restrict__ keep, int ntiles,
        const int32_t* __restrict__ tile_slot, const int32_t* __restrict__ slot_len,
        const int2* __restrict__ slot_cov, const int32_t* __restrict__ cov_ovf,
        int SW, uint32_t* __restrict__ segkept, int32_t* __restrict__ tile_off,
-       int64_t* __restrict__ lengths, int64_t* __restrict__ rec_size,
+       int64_t* __restrict__ lengths, int64_t* __restrict__ rec_size, int32_t* __restrict__ hdr_len,
        int64_t first_idx, int prefix_len)
 {
     extern __shared__ uint32_t plan_sm[];
@@ -111,6 +111,7 @@ k_plan(int64_t S, int FW, const uint32_t* __restrict__ keep, int ntiles,
             lengths[s] = carry;
             const int nd = ndigits_u64((unsigned long long)(first_idx + s + 1));
             rec_size[s] = (int64_t)prefix_len + nd + 1 + carry + 1;   // '>'+prefix, digits, '\n', bases, '\n'
+            hdr_len[s] = prefix_len + nd + 1;                         // k_emit reads it instead of counting digits per visit
         }
     }
 }

@@ -31,6 +31,7 @@ struct EmitParams {
     const int32_t* tile_off;
     const int64_t* lengths;
     const int64_t* rec_off;
+    const int32_t* hdr_len;   // bytes of each record's header line ('>' prefix digits '\n'), from k_plan
     uint8_t* out;
     int64_t s0, s1;
     int64_t first_idx;
@@ -39,7 +40,9 @@ struct EmitParams {
     int rt_cap;            // run-table entries per warp (shared memory)
     int slot_cap;          // slot-table entries staged in shared memory (0: read from global)
     int order;             // CTA -> work mapping: 0 tile-major, 1 sample-major
-    int flat_run_bytes;    // batches whose mean run length is below this take emit_runs_flat (0: never)
+    int flat_run_bytes;    // (sample, tile) visits whose mean run length is below this take the flat form (0: never)
+    int flat_cap;          // FLAT == 2: runs the packed per-warp table of visit_flat holds
+    int flat_bm_words;     // FLAT == 2: words of its vector bitmap
     int debug;             // timing experiments only (wrong output; needs -DGM2_EMIT_DEBUG): 1 no boundary
                            // sectors, 2 no interior stores, 4 interior stores without shared loads
     HeaderPrefix prefix;
@@ -137,6 +140,21 @@ __device__ __forceinline__ void copy_vectors(uint32_t qa, uint8_t* __restrict__ 
         o.w = __funnelshift_r(w[K + 3], w[K + 4], sh);
         st128<POLICY>(d, o);
     }
+}
+
+// One destination-aligned vector per lane, warp-uniform source phase (K, sh): qa as in copy_vectors.
+template <int POLICY, int K>
+__device__ __forceinline__ void copy_one(uint32_t qa, uint8_t* __restrict__ d, int sh)
+{
+    const uint4 lo = lds128(qa);
+    const uint4 hi = lds128(qa + 16);
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint4 o;
+    o.x = __funnelshift_r(w[K], w[K + 1], sh);
+    o.y = __funnelshift_r(w[K + 1], w[K + 2], sh);
+    o.z = __funnelshift_r(w[K + 2], w[K + 3], sh);
+    o.w = __funnelshift_r(w[K + 3], w[K + 4], sh);
+    st128<POLICY>(d, o);
 }
 
 // One batch of kept runs of a (sample, tile): table A entry r = {Q_r, S_r}, entry nr = {end, -}.
@@ -351,10 +369,244 @@ __device__ __forceinline__ void emit_runs_flat(uint32_t tile_a, uint32_t rt_a, i
     __syncwarp();
 }
 
+
+// ------------------------------------------------------------------------------------------
+// visit_flat (FLAT == 2): the whole (sample, tile) visit for SHORT runs, chosen up front from the
+// visit's byte count and its number of runs (both known before any table is built).
+//
+// The work unit is again a destination-aligned 16-byte vector, lane <-> vector, 32 consecutive
+// vectors (one 512-byte row of the output) per warp iteration — the store pattern the memory system
+// wants (profiles/r01_emit_experiments.md).  What the first flat form paid for was FINDING each
+// vector's run (a private linear cursor per lane: ~500 of 2,150 warp instructions per visit at 10 %
+// gene retention) and the byte-wise assembly of vectors that hold a run boundary (~400).  Here:
+//
+//   R space    byte offsets from the 16-byte aligned address at or below the visit's first output
+//              byte; everything fits 16 bits (tile <= 60 KB), so a run is ONE packed word
+//              A[r] = R_r | S_r << 16  (S = source offset in the staged tile), A[nr] = R_end.
+//   events     an "event" is a vector in which at least one run starts.  One pass, lane <-> run,
+//              writes EV[e] = A[last run starting in that vector] (ballot + popc ranks) and sets bit
+//              (R >> 4) of a per-warp bitmap (shared-memory atomic OR).
+//   phase I    row i, lane L: m = BM[i] (broadcast); the vector's run is EV[base + popc(m & lt) - 1
+//              + bit] — no search; it is an interior vector unless its bit is set and the event's run
+//              does not start exactly on it.  Interior: two aligned LDS.128, word select, funnel
+//              shift, one STG.128.  A row whose word is 0 lies inside ONE run: warp-uniform phase, no
+//              selects (copy_vectors).
+//   phase B    same pass as the events, lane <-> run: the first run starting in a vector owns it; up to
+//              three sources (tail of the previous run, one or two starts) are fetched as unaligned
+//              16-byte windows and merged under byte masks; more than three
+//              (runs of a few bytes in a row) fall back to a byte loop.
+//   phase E    the partial first / last vector of the visit (shared with the neighbouring tile's warp),
+//              lane <-> byte.
+// Each vector is written exactly once and whole, boundary vectors a few hundred cycles before the
+// rows around them, i.e. well inside the time the line stays in L2.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tb_load(uint32_t a) {                 // per-warp tables (rewritten per visit)
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tb_store(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tb_or(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+// 16 bytes from an arbitrary shared-memory address: two aligned 128-bit loads, word select, byte funnel shift
+__device__ __forceinline__ uint4 lds_unaligned16(uint32_t a) {
+    const uint32_t qa = a & ~15u;
+    const int sh = (int)(a & 3u) * 8;
+    const uint4 lo = lds128(qa), hi = lds128(qa + 16);
+    uint32_t w0 = lo.x, w1 = lo.y, w2 = lo.z, w3 = lo.w, w4 = hi.x, w5 = hi.y, w6 = hi.z;
+    if (a & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = hi.w; }
+    if (a & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, sh);
+    o.y = __funnelshift_r(w1, w2, sh);
+    o.z = __funnelshift_r(w2, w3, sh);
+    o.w = __funnelshift_r(w3, w4, sh);
+    return o;
+}
+// bytes [0, k) of x, bytes [k, 16) of y  (0 <= k <= 16).  Word w takes its low clamp(8k - 32w, 0, 32) bits from x:
+// the clamped funnel shift turns that bit count into the mask without a table.
+__device__ __forceinline__ uint4 merge16(const uint4& x, const uint4& y, int k) {
+    const int b = 8 * k;
+    const uint32_t m0 = __funnelshift_lc(0xffffffffu, 0u, b);
+    const uint32_t m1 = __funnelshift_lc(0xffffffffu, 0u, max(b - 32, 0));
+    const uint32_t m2 = __funnelshift_lc(0xffffffffu, 0u, max(b - 64, 0));
+    const uint32_t m3 = __funnelshift_lc(0xffffffffu, 0u, max(b - 96, 0));
+    return make_uint4((x.x & m0) | (y.x & ~m0), (x.y & m1) | (y.y & ~m1),
+                      (x.z & m2) | (y.z & ~m2), (x.w & m3) | (y.w & ~m3));
+}
+
+#define FLAT_MAX_TILE 61440          // R and S must fit 16 bits
+
+template <int POLICY>
+__device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32_t ev_a, uint32_t bm_a,
+                                           uint32_t len_a, uint32_t src_a, uint32_t words, int nwords,
+                                           uint8_t* __restrict__ out0 /* first output byte of the visit */,
+                                           int bytes, int lane)
+{
+    uint32_t lt_mask = (1u << lane) - 1u;
+    const int o = (int)((uintptr_t)out0 & 15u);
+    uint8_t* base16 = out0 - o;
+    asm volatile("" : "+l"(base16), "+r"(tile_a), "+r"(lt_mask));       // keep these in registers (no re-derivation per row)
+    const int r_end = o + bytes;
+    const int nbm = ((r_end - 1) >> 9) + 1;                          // rows (= bitmap words) the visit touches
+    for (int i = lane; i < nbm; i += 32) tb_store(bm_a + 4u * i, 0u);
+
+    // ---- table A: one packed word per kept run
+    int nr = 0;
+    {
+        int q = o;
+        uint32_t carry = 0u;
+        for (int c = 0; c < nwords; ++c) {
+            const uint32_t w = __shfl_sync(FULL_MASK, words, c);                  // warp-uniform
+            const int len = (int)lds32(len_a + 4u * (32 * c + lane));
+            const int src = (int)lds32(src_a + 4u * (32 * c + lane));
+            const int x = ((w >> lane) & 1u) ? len : 0;
+            const int incl = warp_incl_scan(x, lane);
+            const uint32_t starts = w & ~((w << 1) | carry);
+            carry = w >> 31;
+            if ((starts >> lane) & 1u)
+                tb_store(a_a + 4u * (nr + __popc(starts & lt_mask)), (uint32_t)(q + incl - x) | ((uint32_t)src << 16));
+            nr += __popc(starts);
+            q += __shfl_sync(FULL_MASK, incl, 31);
+        }
+        if (lane == 0) tb_store(a_a + 4u * nr, (uint32_t)r_end);
+    }
+    __syncwarp();
+
+    // ---- events + phase B, lane <-> run
+    int ne = 0;
+    for (int r0 = 0; r0 < nr; r0 += 32) {
+        const int r = r0 + lane;
+        bool last = false;
+        uint32_t x = 0u;
+        if (r < nr) {
+            x = tb_load(a_a + 4u * r);
+            const int R = (int)(x & 0xffffu), v = R >> 4, p0 = v << 4;
+            const uint32_t x1 = tb_load(a_a + 4u * (r + 1));                      // run r+1, or the end sentinel
+            const bool in1 = r + 1 < nr && (int)((x1 & 0xffffu) >> 4) == v;
+            last = !in1;
+            const uint32_t xm = r > 0 ? tb_load(a_a + 4u * (r - 1)) : 0u;
+            const bool first = r == 0 || (int)((xm & 0xffffu) >> 4) != v;
+            if (first && p0 >= o && p0 + 16 <= r_end && (R > p0 || in1)) {        // this lane owns a boundary vector
+                const uint32_t x2 = r + 2 <= nr ? tb_load(a_a + 4u * (r + 2)) : 0u;
+                const bool in2 = in1 && r + 2 < nr && (int)((x2 & 0xffffu) >> 4) == v;
+                const bool has_prev = R > p0;                                     // then r >= 1: R_0 = o and p0 >= o
+                const int nsrc = (has_prev ? 1 : 0) + 1 + (in1 ? 1 : 0) + (in2 ? 1 : 0);
+                bool slow = nsrc > 3;
+                if (!slow && in2) {                                               // three starts: a fourth would need the loop
+                    const uint32_t x3 = r + 3 <= nr ? tb_load(a_a + 4u * (r + 3)) : 0u;
+                    slow = r + 3 < nr && (int)((x3 & 0xffffu) >> 4) == v;
+                }
+                uint4 ov;
+                if (!slow) {
+                    const uint32_t sa = has_prev ? xm : x, sb = has_prev ? x : x1, sc = has_prev ? x1 : x2;
+                    const uint4 X = lds_unaligned16(tile_a + (sa >> 16) + (uint32_t)(p0 - (int)(sa & 0xffffu)));
+                    const uint4 Y = lds_unaligned16(tile_a + (sb >> 16) + (uint32_t)(p0 - (int)(sb & 0xffffu)));
+                    ov = merge16(X, Y, (int)(sb & 0xffffu) - p0);
+                    if (nsrc == 3) {
+                        const uint4 Z = lds_unaligned16(tile_a + (sc >> 16) + (uint32_t)(p0 - (int)(sc & 0xffffu)));
+                        ov = merge16(ov, Z, (int)(sc & 0xffffu) - p0);
+                    }
+                } else {                                                          // many tiny runs in one vector
+                    int rc = has_prev ? r - 1 : r;
+                    uint32_t xc = tb_load(a_a + 4u * rc);
+                    int rn = (int)(tb_load(a_a + 4u * (rc + 1)) & 0xffffu);
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        while (p0 + j >= rn) { ++rc; xc = tb_load(a_a + 4u * rc); rn = (int)(tb_load(a_a + 4u * (rc + 1)) & 0xffffu); }
+                        w[j >> 2] |= lds8(tile_a + (xc >> 16) + (uint32_t)(p0 + j - (int)(xc & 0xffffu))) << (8 * (j & 3));
+                    }
+                    ov = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                st128<POLICY>(base16 + p0, ov);
+            }
+            if (last) tb_or(bm_a + 4u * (uint32_t)(v >> 5), 1u << (v & 31));
+        }
+        const uint32_t bal = __ballot_sync(FULL_MASK, last);
+        if (last) tb_store(ev_a + 4u * (ne + __popc(bal & lt_mask)), x);
+        ne += __popc(bal);
+    }
+    __syncwarp();
+
+    // ---- phase I: interior vectors, row by row.  The next row's bitmap word and event entry are fetched
+    // before the current row is copied (the table reads are ordered asm statements: nothing else overlaps
+    // their latency with the copy).
+    {
+        int base = 0, i = 0;
+        uint32_t m = tb_load(bm_a);                                               // row 0 always holds event 0 (bit 0)
+        uint32_t e = tb_load(ev_a + 4u * (uint32_t)(__popc(m & lt_mask) - 1 + (int)((m >> lane) & 1u)));
+#pragma unroll 1
+        while (i < nbm) {
+            if (m == 0u && (i << 9) + 512 <= r_end) {
+                // rows i .. i+k-1 lie inside the run of event base-1: warp-uniform source phase, no word select
+                int k = 1;
+                while (i + k < nbm && ((i + k) << 9) + 512 <= r_end && tb_load(bm_a + 4u * (uint32_t)(i + k)) == 0u) ++k;
+                const uint32_t a = tile_a + (e >> 16) + (uint32_t)((i << 9) + (lane << 4) - (int)(e & 0xffffu));
+                const int mis = (int)(a & 15u);                                   // same for every lane: positions are multiples of 16
+                uint8_t* d = base16 + (i << 9) + (lane << 4);
+                const int nb = k << 5, sh = (mis & 3) * 8;
+                const uint32_t qa = a - (uint32_t)mis;
+                if (mis == 0) {
+                    uint32_t q = qa;
+#pragma unroll 1
+                    for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
+                } else {
+                    switch (mis >> 2) {
+                    case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
+                    case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
+                    case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
+                    default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
+                    }
+                }
+                i += k;
+                if (i < nbm) {
+                    m = tb_load(bm_a + 4u * (uint32_t)i);
+                    e = tb_load(ev_a + 4u * (uint32_t)(base + __popc(m & lt_mask) - 1 + (int)((m >> lane) & 1u)));
+                }
+                continue;
+            }
+            const int base_n = base + __popc(m);
+            const uint32_t m_n = i + 1 < nbm ? tb_load(bm_a + 4u * (uint32_t)(i + 1)) : 0u;
+            const uint32_t e_n = tb_load(ev_a + 4u * (uint32_t)(base_n + __popc(m_n & lt_mask) - 1 + (int)((m_n >> lane) & 1u)));
+            const int pos = (i << 9) + (lane << 4);
+            const int R = (int)(e & 0xffffu);
+            if (pos >= o && pos + 16 <= r_end && (((m >> lane) & 1u) == 0u || R == pos))
+                st128<POLICY>(base16 + pos, lds_unaligned16(tile_a + (e >> 16) + (uint32_t)(pos - R)));
+            m = m_n; e = e_n; base = base_n; ++i;
+        }
+    }
+
+    // ---- phase E: the partial first / last vector of the visit, lane <-> byte
+    {
+        const int vl = r_end >> 4;
+        int pos = -1;
+        if (lane < 16) { if (o) pos = lane; }
+        else if ((r_end & 15) && !(o && vl == 0)) pos = (vl << 4) + (lane - 16);
+        if (pos >= o && pos < r_end) {
+            uint32_t xc;
+            if (lane < 16) {
+                int rc = 0; xc = tb_load(a_a);
+                int rn = (int)(tb_load(a_a + 4u) & 0xffffu);
+                while (pos >= rn) { ++rc; xc = tb_load(a_a + 4u * rc); rn = (int)(tb_load(a_a + 4u * (rc + 1)) & 0xffffu); }
+            } else {
+                int rc = nr - 1; xc = tb_load(a_a + 4u * rc);
+                while (pos < (int)(xc & 0xffffu)) { --rc; xc = tb_load(a_a + 4u * rc); }
+            }
+            st8<POLICY>(base16 + pos, lds8(tile_a + (xc >> 16) + (uint32_t)(pos - (int)(xc & 0xffffu))));
+        }
+    }
+    __syncwarp();
+}
+
 #define EMIT_FRONT_PAD 32
 #define EMIT_BACK_PAD  64
 
-template <int POLICY, int MIN_CTAS, int PACK>
+template <int POLICY, int MIN_CTAS, int PACK, int FLAT>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 k_emit(const EmitParams p)
 {
@@ -417,26 +669,30 @@ k_emit(const EmitParams p)
 
     // per-sample metadata is fetched one sample ahead: record offset, this tile's output offset,
     // the sample's length (last tile only) and ALL kept-bit words of the tile in one coalesced load
-    int64_t m_roff = 0; int m_toff = 0; uint32_t m_words = 0u;
+    int64_t m_roff = 0; int m_toff = 0, m_tend = 0, m_hl = 0; uint32_t m_words = 0u;
+    // the flat form needs the tile's slot tables in shared memory and all its kept-bit words in one register per lane
+    const bool flat_ok = FLAT == 2 && PACK == 1 && p.flat_cap > 0 && p.flat_run_bytes > 0 && slots_staged && nwords <= 32;
     auto load_meta = [&](int64_t s) {
         m_roff = __ldg(p.rec_off + s);
+        m_hl = __ldg(p.hdr_len + s);
         if (have_tile) {
             m_toff = __ldg(p.tile_off + (size_t)s * p.ntiles + tile);
+            if (FLAT == 2 && PACK == 1)          // where this tile's output ends: the next tile's offset / the sample's length
+                m_tend = tile == p.ntiles - 1 ? (int)__ldg(p.lengths + s) : __ldg(p.tile_off + (size_t)s * p.ntiles + tile + 1);
             m_words = lane < nwords ? __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + lane) : 0u;
         }
     };
     int64_t s = sb + warp;
     if (s < se) load_meta(s);
     while (s < se) {
-        const int64_t roff = m_roff; const int toff = m_toff; const uint32_t words = m_words;
+        const int64_t roff = m_roff; const int toff = m_toff, tend = m_tend, hl = m_hl; const uint32_t words = m_words;
         const int64_t sn = s + nwarps;
         if (sn < se) load_meta(sn);
 
         uint8_t* rec = p.out + (roff - img0);
-        const unsigned long long num = (unsigned long long)(p.first_idx + s + 1);
-        const int nd = ndigits_u64(num);
-        const int hl = p.prefix.len + nd + 1;
         if (tile == 0) {
+            const unsigned long long num = (unsigned long long)(p.first_idx + s + 1);
+            const int nd = hl - p.prefix.len - 1;
             for (int i = lane; i < hl; i += 32) {
                 char ch;
                 if (i < p.prefix.len) ch = p.prefix.text[i];
@@ -446,7 +702,19 @@ k_emit(const EmitParams p)
             }
         }
         uint8_t* seqout = rec + hl;
-        if (have_tile) {
+        bool flat = false;
+        if (FLAT == 2 && PACK == 1 && flat_ok) {
+            // runs of the visit = run starts in its kept-bit words (lane c holds word c); bytes = tend - toff
+            uint32_t pm = __shfl_up_sync(FULL_MASK, words >> 31, 1);
+            if (lane == 0) pm = 0u;
+            const int nrt = __reduce_add_sync(FULL_MASK, __popc(words & ~((words << 1) | pm)));
+            const int bytes = tend - toff;
+            flat = nrt > 0 && nrt <= p.flat_cap && bytes < nrt * p.flat_run_bytes && ((bytes + 14) >> 9) + 1 <= p.flat_bm_words;
+            if (flat)
+                visit_flat<POLICY>(tile_a, rt_a, rt_a + 4u * (uint32_t)(p.flat_cap + 2), rt_a + 8u * (uint32_t)(p.flat_cap + 2),
+                                   len_a, src_a, words, nwords, seqout + toff, bytes, lane);
+        }
+        if (have_tile && !flat) {
             const int A = (int)((uintptr_t)seqout & 31u);
             uint8_t* base32 = seqout - A;
             asm volatile("" : "+l"(base32));                   // keep the 64-bit base in registers (no re-derivation per run)
@@ -459,7 +727,7 @@ k_emit(const EmitParams p)
                     if (nr > 0) {
                         if (lane == 0) rt_store_x(rt_a + 8u * nr, q);
                         __syncwarp();
-                        if (PACK == 1 && q - rt_load(rt_a).x < nr * p.flat_run_bytes)
+                        if (FLAT == 1 && PACK == 1 && q - rt_load(rt_a).x < nr * p.flat_run_bytes)
                             emit_runs_flat<POLICY>(tile_a, rt_a, nr, base32, lane);
                         else
                             emit_runs<POLICY, PACK>(tile_a, rt_a, rtb_a, nr, base32, lane, p.debug);

@@ -1,16 +1,26 @@
 """Multi-GPU form of the batch entry points: one process per GPU (torchrun), samples sharded.
 
 Samples are independent (minimizer_2.py:469-477 reads only the shared record and the sample's own
-list), so rank r of R takes the contiguous range [r*S//R, (r+1)*S//R): rank order is file order
-and record ids stay global (`first_idx`).  The reference genome is replicated.  The only exchange
-is an all-gather of the per-sample lengths (8 bytes per sample) from which every rank derives the
-global byte offset of its shard; the FASTA bytes never cross NVLink — each rank `pwrite`s its own
-shard into the shared output file.  Backend: NCCL on GPUs, gloo in the CPU tests.
+list), so every rank takes a CONTIGUOUS range of samples: rank order is file order and record ids
+stay global (`first_idx`).  The reference genome is replicated.  The only exchange is an all-gather
+of the per-sample lengths (8 bytes per sample) from which every rank derives the global byte offset
+of its shard; the FASTA bytes never cross NVLink — each rank `pwrite`s its own shard into the shared
+output file.  Backend: NCCL on GPUs, gloo in the CPU tests.
+
+Shards are cut by OUTPUT BYTES, not by sample count: every rank first plans the
+count-based range [r*S//R, (r+1)*S//R) — lengths only, K1-K3, ~0.2 ms per 10,000 samples — the
+lengths are all-gathered, and the ranges are then re-cut at equal cumulative record bytes, so a job
+whose retention drifts along the file (config 4) still finishes on all GPUs at the same time.
+`GM2_SHARD_BALANCE=count` keeps the count-based ranges.
+
+A failure on one rank (bad input, full disk, CUDA error) is agreed on by all ranks before the next
+collective, so no rank is left blocked in an all-gather or barrier: the failing rank re-raises its
+own exception, the others raise RuntimeError naming the step.
 """
 from __future__ import annotations
 
 import os
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -40,16 +50,22 @@ def ensure_process_group() -> None:
     atexit.register(_teardown)
 
 
+_RENDEZVOUS_ENV = ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")
+
+
 def launched_ranks() -> int:
-    """How many ranks share this job: the size of an initialised process group, else torchrun's WORLD_SIZE.
-    GM2_SHARD=0 turns the automatic sharding of the entry functions off (every rank then does the whole job,
-    which is what the reference's CLI would do under torchrun)."""
+    """How many ranks share this job.  Inside an initialised process group: its size.  Otherwise > 1 only for a
+    complete torchrun-style environment (RANK, WORLD_SIZE, MASTER_ADDR and MASTER_PORT all present) — a stray
+    WORLD_SIZE from some other launcher does not switch the entry functions to the sharded path, they then do
+    the whole job as the reference would.  GM2_SHARD=0 turns the automatic sharding off altogether."""
     if os.environ.get("GM2_SHARD", "1") == "0":
         return 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
+    if any(not os.environ.get(k) for k in _RENDEZVOUS_ENV):
+        return 1
     try:
-        return max(int(os.environ.get("WORLD_SIZE", "1")), 1)
+        return max(int(os.environ["WORLD_SIZE"]), 1)
     except ValueError:
         return 1
 
@@ -58,6 +74,17 @@ def _device_for_backend() -> torch.device:
     if dist.get_backend() == "nccl":
         return torch.device("cuda", torch.cuda.current_device())
     return torch.device("cpu")
+
+
+def agree(error: Optional[BaseException], step: str) -> None:
+    """Collective: every rank reports whether `step` succeeded; if any rank failed, ALL ranks raise here
+    (the failing ones their own exception), so nobody enters the next collective alone."""
+    flag = torch.tensor([0 if error is None else 1], dtype=torch.int32, device=_device_for_backend())
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if error is not None:
+        raise error
+    if int(flag.item()):
+        raise RuntimeError(f"genome-minimizer sharded run: another rank failed during '{step}'")
 
 
 def all_gather_lengths(local: np.ndarray) -> List[np.ndarray]:
@@ -81,50 +108,102 @@ def header_len(idx: int) -> int:
     return 1 + len(_engine.SEQ_ID_PREFIX) + len(str(idx + 1)) + 1
 
 
+def record_sizes(lengths: np.ndarray, first_idx: int = 0) -> np.ndarray:
+    """Bytes of every FASTA record: header + bases + '\\n' (minimizer_2.py:476-477), vectorised over samples."""
+    n = int(lengths.size)
+    idx1 = np.arange(first_idx + 1, first_idx + n + 1, dtype=np.int64)
+    digits = np.ones(n, dtype=np.int64)
+    p = 10
+    while n and p <= int(idx1[-1]):
+        digits += idx1 >= p
+        p *= 10
+    return 1 + len(_engine.SEQ_ID_PREFIX) + digits + 1 + np.asarray(lengths, dtype=np.int64) + 1
+
+
+def balance_mode() -> str:
+    return "count" if os.environ.get("GM2_SHARD_BALANCE", "bytes") == "count" else "bytes"
+
+
+def pwrite_all(fd: int, view: np.ndarray, pos: int) -> int:
+    """os.pwrite until every byte is down (a single write may be short: ENOSPC part-way, a signal, or the
+    kernel's 0x7ffff000 per-call cap).  Returns the position after the last byte."""
+    mv = memoryview(view).cast("B")
+    while len(mv):
+        k = os.pwrite(fd, mv, pos)
+        if k <= 0:
+            raise OSError(f"pwrite wrote {k} bytes at offset {pos} ({len(mv)} left)")
+        pos += k
+        mv = mv[k:]
+    return pos
+
+
+def _planned_lengths(eng, all_lists: Sequence, n: int, rank: int, world: int) -> Tuple[np.ndarray, int, int, bool]:
+    """Plan the count-based range, all-gather the lengths, choose the final contiguous range of this rank.
+    Returns (all n lengths, lo, hi, replan) — replan says the engine's current plan is for another range."""
+    lo, hi = _engine.shard_range(n, rank, world)
+    err, local_len = None, np.zeros(0, dtype=np.int64)
+    try:
+        local_len = np.asarray(eng.plan_lists(all_lists[lo:hi], first_idx=lo), dtype=np.int64)
+    except BaseException as e:  # noqa: BLE001 - agreed on below, then re-raised
+        err = e
+    agree(err, "plan")
+    gathered = all_gather_lengths(local_len)
+    lengths = np.concatenate(gathered) if gathered else np.zeros(0, dtype=np.int64)
+    assert lengths.size == n
+    if balance_mode() == "bytes" and world > 1:
+        lo2, hi2 = _engine.shard_range_by_bytes(record_sizes(lengths), rank, world)
+        return lengths, lo2, hi2, (lo2, hi2) != (lo, hi)
+    return lengths, lo, hi, False
+
+
 def run_single_file_sharded(record, all_lists: Sequence, model_name: str, output_file: str,
                             make_engine: Optional[Callable[[], object]] = None,
-                            timestamp: Optional[str] = None) -> dict:
+                            timestamp: Optional[str] = None, quiet: bool = False) -> dict:
     """`process_multiple_genomes_single_file` (reference :447-495) over all ranks of the default
-    process group.  Every rank returns the same dict; rank 0 prints the progress lines."""
+    process group.  Every rank returns the same dict; rank 0 prints the progress lines.  All ranks must see
+    `output_file` on one shared filesystem (rank 0 creates and sizes it, every rank writes its own part)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     n = len(all_lists)
     G = len(record.seq)
-    lo, hi = _engine.shard_range(n, rank, world)
     eng = make_engine() if make_engine is not None else _engine.MinimizerEngine(record)
     try:
-        local_len = eng.plan_lists(all_lists[lo:hi], first_idx=lo)
-        gathered = all_gather_lengths(np.asarray(local_len, dtype=np.int64))
-        lengths = np.concatenate(gathered) if gathered else np.zeros(0, dtype=np.int64)
-        assert lengths.size == n
-        rec_sizes = np.asarray([header_len(i) for i in range(n)], dtype=np.int64) + lengths + 1
+        lengths, lo, hi, replan = _planned_lengths(eng, all_lists, n, rank, world)
         pre = (f"# Minimized genomes generated using model: {model_name}\n"
                f"# Total genomes: {n}\n"
                f"# Generated on: {timestamp if timestamp is not None else np.datetime64('now')}\n").encode()
         rec_off = np.zeros(n + 1, dtype=np.int64)
-        rec_off[1:] = np.cumsum(rec_sizes)
-        if rank == 0:
-            with open(output_file, "wb") as fh:
-                fh.write(pre)
-                fh.truncate(len(pre) + int(rec_off[-1]))
-        dist.barrier()
-        fd = os.open(output_file, os.O_WRONLY)
+        rec_off[1:] = np.cumsum(record_sizes(lengths))
+        err = None
         try:
-            base = len(pre) + int(rec_off[lo])
-            pos = [base]
+            if rank == 0:
+                with open(output_file, "wb") as fh:
+                    fh.write(pre)
+                    fh.truncate(len(pre) + int(rec_off[-1]))
+            if replan:
+                eng.plan_lists(all_lists[lo:hi], first_idx=lo)
+        except BaseException as e:  # noqa: BLE001
+            err = e
+        agree(err, "create output file")
+        try:
+            fd = os.open(output_file, os.O_WRONLY)
+            try:
+                pos = [len(pre) + int(rec_off[lo])]
 
-            def sink(sa: int, sb: int, view: np.ndarray) -> None:
-                os.pwrite(fd, view, pos[0])
-                pos[0] += view.size
+                def sink(sa: int, sb: int, view: np.ndarray) -> None:
+                    pos[0] = pwrite_all(fd, view, pos[0])
 
-            eng.drain(sink)
-            assert pos[0] == len(pre) + int(rec_off[hi])
-        finally:
-            os.close(fd)
-        dist.barrier()
+                eng.drain(sink)
+                if pos[0] != len(pre) + int(rec_off[hi]):
+                    raise RuntimeError(f"rank {rank} wrote up to byte {pos[0]}, expected {len(pre) + int(rec_off[hi])}")
+            finally:
+                os.close(fd)
+        except BaseException as e:  # noqa: BLE001
+            err = e
+        agree(err, "write shard")                     # doubles as the closing barrier
     finally:
         if make_engine is None:
             eng.close()
-    if rank == 0:
+    if rank == 0 and not quiet:
         for idx in range(n):
             print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
             if _engine._sampled(idx):
@@ -140,38 +219,44 @@ def run_single_file_sharded(record, all_lists: Sequence, model_name: str, output
 
 def run_multi_file_sharded(record, all_lists: Sequence, model_name: str, output_dir,
                            filename_template: str = "minimized_{model}_{idx:04d}.fasta",
-                           make_engine: Optional[Callable[[], object]] = None) -> dict:
+                           make_engine: Optional[Callable[[], object]] = None, quiet: bool = False) -> dict:
     """`process_multiple_genomes_multiple_files` (reference :499-560) over all ranks: every rank writes
     the files of its own contiguous shard (global idx in the names and record ids); the lengths are
     all-gathered so that every rank returns the reference's dict and rank 0 prints its lines."""
     rank, world = dist.get_rank(), dist.get_world_size()
     n = len(all_lists)
     G = len(record.seq)
-    lo, hi = _engine.shard_range(n, rank, world)
-    if rank == 0:
-        os.makedirs(output_dir, exist_ok=True)
-    dist.barrier()
+    err = None
+    try:
+        if rank == 0:
+            os.makedirs(output_dir, exist_ok=True)
+    except BaseException as e:  # noqa: BLE001
+        err = e
+    agree(err, "create output directory")
     eng = make_engine() if make_engine is not None else _engine.MinimizerEngine(record)
     try:
-        local_len = np.asarray(eng.plan_lists(all_lists[lo:hi], first_idx=lo), dtype=np.int64)
-        sizes = np.asarray([header_len(lo + i) for i in range(hi - lo)], dtype=np.int64) + local_len + 1
-        rel = np.zeros(hi - lo + 1, dtype=np.int64)
-        rel[1:] = np.cumsum(sizes)
+        lengths, lo, hi, replan = _planned_lengths(eng, all_lists, n, rank, world)
+        try:
+            if replan:
+                eng.plan_lists(all_lists[lo:hi], first_idx=lo)
+            rel = np.zeros(hi - lo + 1, dtype=np.int64)
+            rel[1:] = np.cumsum(record_sizes(lengths[lo:hi], first_idx=lo))
 
-        def sink(sa: int, sb: int, view: np.ndarray) -> None:
-            base = int(rel[sa])
-            for s in range(sa, sb):
-                fname = filename_template.format(model=model_name, idx=lo + s)
-                with open(os.path.join(output_dir, fname), "wb") as fh:
-                    fh.write(view[int(rel[s]) - base:int(rel[s + 1]) - base])
+            def sink(sa: int, sb: int, view: np.ndarray) -> None:
+                base = int(rel[sa])
+                for s in range(sa, sb):
+                    fname = filename_template.format(model=model_name, idx=lo + s)
+                    with open(os.path.join(output_dir, fname), "wb") as fh:
+                        fh.write(view[int(rel[s]) - base:int(rel[s + 1]) - base])
 
-        eng.drain(sink)
-        lengths = np.concatenate(all_gather_lengths(local_len)) if n else np.zeros(0, dtype=np.int64)
-        dist.barrier()
+            eng.drain(sink)
+        except BaseException as e:  # noqa: BLE001
+            err = e
+        agree(err, "write shard")
     finally:
         if make_engine is None:
             eng.close()
-    if rank == 0:
+    if rank == 0 and not quiet:
         print(f"Writing {n} individual FASTA files to: {output_dir}")
         for idx in range(n):
             print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")

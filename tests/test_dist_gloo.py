@@ -192,7 +192,13 @@ def test_entry_function_shards_by_itself_multi_file(tmp_path):
 
 def test_gm2_shard_0_keeps_the_whole_job_in_every_rank(monkeypatch):
     from genome_minimizer_2_b200 import dist as gdist, minimizer_2 as m2
+    for k in ("RANK", "MASTER_ADDR", "MASTER_PORT"):
+        monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("WORLD_SIZE", "4")
+    assert m2._ranks() == 1 and gdist.launched_ranks() == 1      # a stray WORLD_SIZE is not a torchrun job
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("MASTER_PORT", "29500")
     assert m2._ranks() == 4 and gdist.launched_ranks() == 4
     monkeypatch.setenv("GM2_SHARD", "0")
     assert m2._ranks() == 1

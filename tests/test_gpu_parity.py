@@ -318,17 +318,53 @@ def test_dense_tiny_genes_exercise_table_flush_and_global_slot_path():
     S = 21
     rows = synth.pack_keep_rows(rng.random((S, F)) < np.linspace(0.05, 0.95, S)[:, None])
     exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows)
-    for rt_cap, warps, flat in ((32, 8, 0), (64, 4, 640), (1024, 2, 1 << 20), (32, 8, 1 << 20), (1024, 1, 0)):
+    for rt_cap, warps, flat, mode in ((32, 8, 0, 2), (64, 4, 640, 1), (1024, 2, 1 << 20, 1), (32, 8, 1 << 20, 1), (1024, 1, 0, 1),
+                                      (64, 4, 640, 2), (1024, 2, 1 << 20, 2), (32, 8, 1 << 20, 2)):
         with _native.Context(0) as ctx:
             ctx.configure(_native.CFG_RUN_TABLE, rt_cap)
             ctx.configure(_native.CFG_EMIT_WARPS, warps)
             ctx.configure(_native.CFG_FLAT_RUN_BYTES, flat)
+            ctx.configure(_native.CFG_FLAT_MODE, mode)
             ctx.set_reference(seq, starts, ends)
             assert ctx.query(_native.Q_NUM_SLOTS) > 4096
             ctx.load_keep_host(rows)
             ctx.plan(0)
             assert np.array_equal(ctx.lengths(), exp_len)
             assert np.array_equal(_gpu_image(ctx, S), exp_img)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_short_run_visits_match_the_oracle(mode):
+    """Low gene retention on gene-shaped genomes: most kept runs are intergenic gaps of a few bytes to a few
+    hundred bytes, the case the flat emit forms exist for (GM2_CFG_FLAT_MODE).  Gaps are exponential with a
+    small mean so that vectors holding two, three and more run starts, runs shorter than one vector, visits
+    that start / end inside a vector and visits with no run at all occur; retention ramps from 0 to 0.6 over
+    the samples; default tile and a small one; both launch forms; always-flat and the default threshold."""
+    rng = np.random.default_rng(77 + mode)
+    for G, F, gap_mean, tile in ((400_000, 900, 40, 0), (300_000, 260, 120, 0), (90_000, 700, 6, 8192), (120_000, 40, 300, 16384)):
+        lens = np.maximum(rng.lognormal(np.log(G / F * 0.8), 0.5, F).astype(np.int64), 1)
+        gaps = rng.exponential(gap_mean, F).astype(np.int64)
+        gaps[rng.random(F) < 0.15] = 0                       # abutting genes
+        starts = np.cumsum(gaps + np.concatenate([[0], lens[:-1]]))
+        ends = np.minimum(starts + lens, G)
+        starts = np.minimum(starts, G)
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G)]
+        S = 40
+        keep = rng.random((S, F)) < np.linspace(0.0, 0.6, S)[:, None]
+        rows = synth.pack_keep_rows(keep)
+        exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows, first_idx=7)
+        for occ, frb in ((4, 640), (3, 1 << 20), (0, 200)):
+            with _native.Context(0) as ctx:
+                if tile:
+                    ctx.configure(_native.CFG_TILE_BYTES, tile)
+                ctx.configure(_native.CFG_FLAT_MODE, mode)
+                ctx.configure(_native.CFG_EMIT_OCCUPANCY, occ)
+                ctx.configure(_native.CFG_FLAT_RUN_BYTES, frb)
+                ctx.set_reference(seq, starts, ends)
+                ctx.load_keep_host(rows)
+                ctx.plan(7)
+                assert np.array_equal(ctx.lengths(), exp_len)
+                assert np.array_equal(_gpu_image(ctx, S), exp_img), (G, F, tile, occ, frb)
 
 
 def test_many_genes_cover_one_segment():
@@ -543,6 +579,7 @@ def test_fuzz_kernel_configurations():
             _native.CFG_EMIT_BATCH: int(rng.choice([0, 1, 3, 16])),
             _native.CFG_FLAT_RUN_BYTES: int(rng.choice([0, 64, 640, 1 << 20])),
             _native.CFG_EMIT_OCCUPANCY: int(rng.choice([0, 3, 4])),
+            _native.CFG_FLAT_MODE: int(rng.choice([0, 1, 2])),
         }
         with _native.Context(0) as ctx:
             for k, v in cfg.items():

@@ -63,6 +63,17 @@ def test_three_restatements_agree(case):
         assert image[pos:pos + len(r)].tobytes() == r and int(lengths[s]) == len(lit)
         pos += len(r)
     assert pos == image.size
+    # the many-samples length form (used by bench.py to check every length of a 100,000-sample job)
+    assert np.array_equal(mo.kept_lengths_numpy(len(seq), starts, ends, keep), lengths)
+
+
+def test_vectorised_lengths_agree_with_the_mask_form_on_a_gene_shaped_genome():
+    g = synth.make_genome(150_000, 140, seed=11, nested=6, overlap_frac=0.4, join_genes=3, origin_wrap=True)
+    starts, ends = g.starts_ends()
+    rng = np.random.default_rng(5)
+    keep = rng.random((37, len(starts))) < rng.random((37, 1))
+    exp = [int(mo.kept_mask_numpy(g.G, starts, ends, k).sum()) for k in keep]
+    assert mo.kept_lengths_numpy(g.G, starts, ends, keep, chunk=8).tolist() == exp
 
 
 @settings(max_examples=150, deadline=None)

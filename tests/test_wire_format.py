@@ -2,8 +2,8 @@
 
 gm2_emit_host may ship kept bases as 2 bits each and expand them on the host (host_expand.cpp).  Here
 the wire format is produced by numpy from a known image, exactly as include/gm2.h describes it, and the
-decoder must give back the image byte for byte — scalar and AVX2 forms, any destination alignment, one
-and many threads.  (The GPU side of the format, k_emit_packed, is covered by the -m gpu tests, which
+decoder must give back the image byte for byte — scalar, AVX2 and AVX-512 VBMI forms (a level the CPU
+lacks falls back to the next one down), any destination alignment, one and many threads.  (The GPU side of the format, k_emit_packed, is covered by the -m gpu tests, which
 compare both transports with the oracle.)"""
 import ctypes
 
@@ -54,8 +54,8 @@ def _pack_chunk(seqs, tile_lens, ntiles, first_idx):
 def _decode(packed, tile_off, rec_off, lengths, ntiles, first_idx, threads, simd, misalign=0):
     lib = _native.load()
     total = int(rec_off[-1])
-    raw = np.full(total + 64 + misalign, 0x2a, dtype=np.uint8)
-    base = (-raw.ctypes.data) % 32 + misalign                   # choose the destination's alignment
+    raw = np.full(total + 128 + misalign, 0x2a, dtype=np.uint8)
+    base = (-raw.ctypes.data) % 64 + misalign                   # choose the destination's alignment
     out = raw[base:base + total]
     rc = lib.gm2_diag_expand(packed.ctypes.data, tile_off.ctypes.data, rec_off.ctypes.data, lengths.ctypes.data,
                              len(lengths), ntiles, first_idx, PREFIX.encode(), out.ctypes.data, threads, simd)
@@ -65,7 +65,7 @@ def _decode(packed, tile_off, rec_off, lengths, ntiles, first_idx, threads, simd
     return out.tobytes()
 
 
-@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("simd", [0, 1, 2, 3])
 @pytest.mark.parametrize("threads", [1, 3])
 def test_decoder_round_trip(simd, threads):
     rng = np.random.default_rng(7 + simd + 10 * threads)
@@ -74,14 +74,14 @@ def test_decoder_round_trip(simd, threads):
         S = int(rng.integers(1, 12))
         seqs, tile_lens = [], []
         for _ in range(S):
-            tl = [int(x) for x in rng.choice([0, 1, 15, 16, 17, 31, 95, 96, 97, 128, 1000, 4097], size=ntiles)]
+            tl = [int(x) for x in rng.choice([0, 1, 15, 16, 17, 31, 95, 96, 97, 128, 255, 256, 257, 320, 1000, 4097], size=ntiles)]
             if rng.random() < 0.2:
                 tl = [0] * ntiles                                               # everything deleted: ">id\n\n"
             tile_lens.append(tl)
             seqs.append(bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=sum(tl))))
         first = int(rng.choice([0, 8, 99, 999_999]))
         packed, tile_off, rec_off, lengths, image = _pack_chunk(seqs, tile_lens, ntiles, first)
-        for misalign in (0, 1, 13, 31):
+        for misalign in (0, 1, 13, 31, 33, 63):
             got = _decode(packed, tile_off, rec_off, lengths, ntiles, first, threads, simd, misalign)
             assert got == image, (trial, misalign)
 
@@ -92,7 +92,8 @@ def test_decoder_large_pieces_many_threads():
     tile_lens = [[int(x) for x in rng.integers(0, 50_000, ntiles)] for _ in range(S)]
     seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=sum(tl))) for tl in tile_lens]
     packed, tile_off, rec_off, lengths, image = _pack_chunk(seqs, tile_lens, ntiles, 0)
-    assert _decode(packed, tile_off, rec_off, lengths, ntiles, 0, 8, 1) == image
+    for simd in (1, 2, 3):
+        assert _decode(packed, tile_off, rec_off, lengths, ntiles, 0, 8, simd) == image
     assert _decode(packed, tile_off, rec_off, lengths, ntiles, 0, 1, 0) == image
 
 
