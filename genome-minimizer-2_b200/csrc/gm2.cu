@@ -56,8 +56,8 @@ struct gm2_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;        // where work is issued (own or adopted)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_emit[2] = {nullptr, nullptr};
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_emit[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
     std::string err;
     uint64_t launches = 0;
 
@@ -132,8 +132,9 @@ struct gm2_ctx {
     // staging for gm2_emit_host
     uint8_t* d_stage[2] = {nullptr, nullptr}; int64_t stage_cap = 0;
     // two-bit wire format (k_emit_packed -> pinned host staging -> host_expand): device / pinned words, tile_off rows
-    uint32_t* d_pstage[2] = {nullptr, nullptr}; uint32_t* h_pstage[2] = {nullptr, nullptr}; int64_t pstage_words = 0;
-    int32_t* h_toff[2] = {nullptr, nullptr}; int64_t h_toff_cap = 0;
+    uint32_t* d_pstage[3] = {nullptr, nullptr, nullptr}; uint32_t* h_pstage[3] = {nullptr, nullptr, nullptr}; int64_t pstage_words = 0;
+    int32_t* h_toff[3] = {nullptr, nullptr, nullptr}; int64_t h_toff_cap = 0;
+    bool packed_attr_set = false; size_t packed_attr_smem = 0;
     gm2host::Pool* pool = nullptr;     // expansion workers, created on first use
     int64_t last_d2h_bytes = 0;        // device->host bytes moved by the last gm2_emit_host
     int last_wire = 1;                 // wire format it used
@@ -233,7 +234,7 @@ GM2_API int gm2_create(int device, gm2_ctx** out) {
         cuda_fail(nullptr, e, "gm2_create: cudaStreamCreate"); delete c; return GM2_ERR_CUDA;
     }
     c->stream = c->own_stream;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         cudaEventCreateWithFlags(&c->ev_emit[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
     }
@@ -260,12 +261,12 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->ev_total) cudaEventDestroy(c->ev_total);
     delete c->pool;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
         if (c->h_pstage[i]) cudaFreeHost(c->h_pstage[i]);
         if (c->h_toff[i]) cudaFreeHost(c->h_toff[i]);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (c->ev_emit[i]) cudaEventDestroy(c->ev_emit[i]);
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     }
@@ -899,7 +900,10 @@ static int launch_emit_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint32_t* dev_
     p.order = c->order;
     const size_t sm = 32 + (size_t)(c->tile_bytes / 4) + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (p.rt_cap + 2) * 8;
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit_host: shared memory budget exceeded; lower tile bytes / emit warps");
-    CU(c, cudaFuncSetAttribute(k_emit_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    if (!c->packed_attr_set || c->packed_attr_smem != sm) {       // once per configuration, not per chunk
+        CU(c, cudaFuncSetAttribute(k_emit_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        c->packed_attr_set = true; c->packed_attr_smem = sm;
+    }
     k_emit_packed<<<(unsigned)blocks, warps * 32, sm, c->stream>>>(p);
     LAUNCH_CHECK(c, "k_emit_packed");
     return GM2_OK;
@@ -925,13 +929,13 @@ static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_ou
     }
     if (max_words > c->pstage_words) {
         CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->copy_stream));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
             if (c->h_pstage[i]) cudaFreeHost(c->h_pstage[i]);
             c->d_pstage[i] = nullptr; c->h_pstage[i] = nullptr;
         }
         c->pstage_words = 0;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             CU(c, cudaMalloc((void**)&c->d_pstage[i], (size_t)max_words * 4));
             CU(c, cudaMallocHost((void**)&c->h_pstage[i], (size_t)max_words * 4 + 64));    // + the decoder's over-read
         }
@@ -939,30 +943,22 @@ static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_ou
     }
     if (max_rows * nt > c->h_toff_cap) {
         CU(c, cudaStreamSynchronize(c->copy_stream));
-        for (int i = 0; i < 2; ++i) { if (c->h_toff[i]) cudaFreeHost(c->h_toff[i]); c->h_toff[i] = nullptr; }
+        for (int i = 0; i < 3; ++i) { if (c->h_toff[i]) cudaFreeHost(c->h_toff[i]); c->h_toff[i] = nullptr; }
         c->h_toff_cap = 0;
-        for (int i = 0; i < 2; ++i) CU(c, cudaMallocHost((void**)&c->h_toff[i], (size_t)(max_rows * nt) * 4));
+        for (int i = 0; i < 3; ++i) CU(c, cudaMallocHost((void**)&c->h_toff[i], (size_t)(max_rows * nt) * 4));
         c->h_toff_cap = max_rows * nt;
     }
-    auto expand = [&](size_t i) -> int {
-        const int buf = (int)(i & 1);
-        CU(c, cudaEventSynchronize(c->ev_copy[buf]));
-        gm2host::ChunkView v;
-        v.packed = c->h_pstage[buf]; v.tile_off = c->h_toff[buf]; v.rec_off = c->h_rec_off; v.lengths = c->h_len;
-        v.out = host_out + (c->h_rec_off[chunks[i].first] - c->h_rec_off[s0]);
-        v.s0 = chunks[i].first; v.s1 = chunks[i].second; v.first_idx = c->first_idx; v.ntiles = nt;
-        v.prefix = c->prefix.text; v.prefix_len = c->prefix.len; v.simd = 1;
-        c->pool->expand_chunk(v);
-        return GM2_OK;
-    };
-    int rc;
-    for (size_t i = 0; i < chunks.size(); ++i) {
-        const int buf = (int)(i & 1);
+    // Three staging buffers: the GPU side (k_emit_packed + the two copies of a chunk) runs up to two chunks ahead
+    // of the expansion.  Per chunk the caller's thread waits for the chunk's copy, starts the expansion workers,
+    // enqueues the GPU work of the chunk two ahead WHILE they decode, and then decodes with them.
+    auto enqueue = [&](size_t i) -> int {
+        const int buf = (int)(i % 3);
         const int64_t a = chunks[i].first, b = chunks[i].second;
-        // d_pstage[buf] / h_pstage[buf] were last used by chunk i-2: its copy is ordered by the event, its
-        // expansion finished on this thread before chunk i-1 was launched
-        if (i >= 2) CU(c, cudaStreamWaitEvent(c->stream, c->ev_copy[buf], 0));
-        if ((rc = launch_emit_packed(c, a, b, c->d_pstage[buf]))) return rc;
+        // d_pstage[buf] / h_pstage[buf] were last used by chunk i-3: its copy is ordered by the event, its
+        // expansion finished on this thread before this call
+        if (i >= 3) CU(c, cudaStreamWaitEvent(c->stream, c->ev_copy[buf], 0));
+        int rc2 = launch_emit_packed(c, a, b, c->d_pstage[buf]);
+        if (rc2) return rc2;
         CU(c, cudaEventRecord(c->ev_emit[buf], c->stream));
         CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_emit[buf], 0));
         const int64_t words = packed_words(c, a, b), rows = (b - a) * nt;
@@ -970,9 +966,23 @@ static int emit_host_packed(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_ou
         CU(c, cudaMemcpyAsync(c->h_toff[buf], c->d_tile_off + (size_t)a * nt, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->copy_stream));
         CU(c, cudaEventRecord(c->ev_copy[buf], c->copy_stream));
         c->last_d2h_bytes += words * 4 + rows * 4;
-        if (i >= 1 && (rc = expand(i - 1))) return rc;
+        return GM2_OK;
+    };
+    int rc;
+    for (size_t i = 0; i < chunks.size() && i < 2; ++i) if ((rc = enqueue(i))) return rc;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        const int buf = (int)(i % 3);
+        CU(c, cudaEventSynchronize(c->ev_copy[buf]));
+        gm2host::ChunkView v;
+        v.packed = c->h_pstage[buf]; v.tile_off = c->h_toff[buf]; v.rec_off = c->h_rec_off; v.lengths = c->h_len;
+        v.out = host_out + (c->h_rec_off[chunks[i].first] - c->h_rec_off[s0]);
+        v.s0 = chunks[i].first; v.s1 = chunks[i].second; v.first_idx = c->first_idx; v.ntiles = nt;
+        v.prefix = c->prefix.text; v.prefix_len = c->prefix.len; v.simd = 1;
+        c->pool->start(v);
+        rc = i + 2 < chunks.size() ? enqueue(i + 2) : GM2_OK;
+        c->pool->finish();
+        if (rc) return rc;
     }
-    if (!chunks.empty() && (rc = expand(chunks.size() - 1))) return rc;
     CU(c, cudaStreamSynchronize(c->copy_stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return GM2_OK;

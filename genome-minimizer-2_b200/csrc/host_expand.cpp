@@ -163,36 +163,48 @@ static void expand_task(const ChunkView& v, int64_t task) {
     if (part == TASKS_PER_SAMPLE - 1) seq[len] = '\n';
 }
 
-// ---- persistent workers: a chunk is decoded every few milliseconds, thread start-up would show -----
+// ---- persistent workers: a chunk is decoded every ~100 microseconds, so workers first SPIN on the job
+// generation for a short while (a futex wake-up costs 10-30 us per thread) and only then sleep ----------
 struct Pool::Impl {
     std::vector<std::thread> workers;
     std::mutex m;
     std::condition_variable wake, done;
-    const ChunkView* job = nullptr;
+    ChunkView job;
     int64_t ntasks = 0;
     std::atomic<int64_t> next{0};
-    int active = 0;                 // workers still inside the current job
-    uint64_t generation = 0;
-    bool stop = false;
+    std::atomic<int> active{0};             // workers still inside the current job
+    std::atomic<uint64_t> generation{0};
+    std::atomic<bool> stop{false};
+    int sleepers = 0;                       // workers blocked on `wake` (under m)
+    bool running = false;
+
+    static constexpr int SPIN = 20000;      // ~100-200 us of pause instructions
 
     void drain() {
         for (;;) {
             const int64_t t = next.fetch_add(1, std::memory_order_relaxed);
             if (t >= ntasks) break;
-            expand_task(*job, t);
+            expand_task(job, t);
         }
     }
     void worker() {
         uint64_t seen = 0;
-        std::unique_lock<std::mutex> lk(m);
         for (;;) {
-            wake.wait(lk, [&] { return stop || generation != seen; });
-            if (stop) return;
-            seen = generation;
-            lk.unlock();
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
+                if (++spins < SPIN) { _mm_pause(); continue; }
+                std::unique_lock<std::mutex> lk(m);
+                ++sleepers;
+                wake.wait(lk, [&] { return stop.load() || generation.load(std::memory_order_acquire) != seen; });
+                --sleepers;
+            }
+            if (stop.load(std::memory_order_relaxed)) return;
+            seen = generation.load(std::memory_order_acquire);
             drain();
-            lk.lock();
-            if (--active == 0) done.notify_one();
+            if (active.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                std::lock_guard<std::mutex> lk(m);
+                done.notify_one();
+            }
         }
     }
 };
@@ -235,28 +247,48 @@ Pool::Pool(int threads) : impl_(new Impl), threads_(threads < 1 ? 1 : threads) {
 Pool::~Pool() {
     {
         std::lock_guard<std::mutex> lk(impl_->m);
-        impl_->stop = true;
+        impl_->stop.store(true);
     }
     impl_->wake.notify_all();
     for (auto& th : impl_->workers) th.join();
     delete impl_;
 }
 
-void Pool::expand_chunk(const ChunkView& v) {
-    const int64_t n = (v.s1 - v.s0) * TASKS_PER_SAMPLE;
-    if (n <= 0) return;
+// Publish a chunk and return at once: the workers start decoding while the caller does something else
+// (enqueueing the next chunk's GPU work); finish() makes the caller take tasks too and waits for the rest.
+void Pool::start(const ChunkView& v) {
     Impl& p = *impl_;
+    p.job = v;
+    p.ntasks = (v.s1 - v.s0) * TASKS_PER_SAMPLE;
+    p.next.store(0, std::memory_order_relaxed);
+    p.active.store((int)p.workers.size(), std::memory_order_relaxed);
+    p.running = true;
+    p.generation.fetch_add(1, std::memory_order_release);
+    bool wake_needed;
     {
         std::lock_guard<std::mutex> lk(p.m);
-        p.job = &v; p.ntasks = n; p.next.store(0, std::memory_order_relaxed);
-        p.active = (int)p.workers.size();
-        ++p.generation;
+        wake_needed = p.sleepers > 0;
     }
-    p.wake.notify_all();
+    if (wake_needed) p.wake.notify_all();
+}
+
+void Pool::finish() {
+    Impl& p = *impl_;
+    if (!p.running) return;
     p.drain();                                             // the calling thread works too
-    std::unique_lock<std::mutex> lk(p.m);
-    p.done.wait(lk, [&] { return p.active == 0; });
-    p.job = nullptr;
+    int spins = 0;
+    while (p.active.load(std::memory_order_acquire) != 0) {
+        if (++spins < Impl::SPIN) { _mm_pause(); continue; }
+        std::unique_lock<std::mutex> lk(p.m);
+        p.done.wait(lk, [&] { return p.active.load(std::memory_order_acquire) == 0; });
+    }
+    p.running = false;
+}
+
+void Pool::expand_chunk(const ChunkView& v) {
+    if (v.s1 <= v.s0) return;
+    start(v);
+    finish();
 }
 
 void expand_chunk(const ChunkView& v, int threads) {

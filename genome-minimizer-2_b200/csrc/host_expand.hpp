@@ -41,7 +41,9 @@ public:
     ~Pool();
     Pool(const Pool&) = delete;
     Pool& operator=(const Pool&) = delete;
-    void expand_chunk(const ChunkView& v);
+    void expand_chunk(const ChunkView& v);      // start + finish
+    void start(const ChunkView& v);             // workers begin at once; the view is copied
+    void finish();                              // the caller helps, then waits for the workers
     int threads() const { return threads_; }
 private:
     struct Impl;
