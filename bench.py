@@ -693,8 +693,11 @@ def sharded_file_leg(g, table, job: Job, rank, world, barrier, gb_per_rank):
                 raise SystemExit("bench.py: sharded file leg differs from the oracle")
             res = {"samples": n, "full_job": n == job.total, "file_bytes": int(file_size), "seconds": dt,
                    "gbp_per_s": float(lengths.sum()) / dt / 1e9, "balance": gdist.balance_mode(),
-                   "api": ("dist.run_single_file_sharded (NCCL; each rank pwrites its shard)" if world > 1
-                           else "engine.run_single_file (one process)"),
+                   "api": ("dist.run_single_file_sharded (NCCL; each rank produces its shard" if world > 1
+                           else "engine.run_single_file (one process; records produced") +
+                          (" with pwrite)" if os.environ.get("GM2_FILE_SINK", "map") == "write"
+                           else " straight into a shared mapping of the file)"),
+                   "gb_per_s_file": file_size / dt / 1e9,
                    "target": out.rsplit("/", 2)[0] + "/… (tmpfs)" if out.startswith("/dev/shm") else "temp dir",
                    "lengths_checked": n, "records_checked": len(picks), "byte_identical": True}
         barrier()

@@ -124,17 +124,7 @@ def balance_mode() -> str:
     return "count" if os.environ.get("GM2_SHARD_BALANCE", "bytes") == "count" else "bytes"
 
 
-def pwrite_all(fd: int, view: np.ndarray, pos: int) -> int:
-    """os.pwrite until every byte is down (a single write may be short: ENOSPC part-way, a signal, or the
-    kernel's 0x7ffff000 per-call cap).  Returns the position after the last byte."""
-    mv = memoryview(view).cast("B")
-    while len(mv):
-        k = os.pwrite(fd, mv, pos)
-        if k <= 0:
-            raise OSError(f"pwrite wrote {k} bytes at offset {pos} ({len(mv)} left)")
-        pos += k
-        mv = mv[k:]
-    return pos
+pwrite_all = _engine.pwrite_all
 
 
 def _planned_lengths(eng, all_lists: Sequence, n: int, rank: int, world: int) -> Tuple[np.ndarray, int, int, bool]:
@@ -185,18 +175,9 @@ def run_single_file_sharded(record, all_lists: Sequence, model_name: str, output
             err = e
         agree(err, "create output file")
         try:
-            fd = os.open(output_file, os.O_WRONLY)
-            try:
-                pos = [len(pre) + int(rec_off[lo])]
-
-                def sink(sa: int, sb: int, view: np.ndarray) -> None:
-                    pos[0] = pwrite_all(fd, view, pos[0])
-
-                eng.drain(sink)
-                if pos[0] != len(pre) + int(rec_off[hi]):
-                    raise RuntimeError(f"rank {rank} wrote up to byte {pos[0]}, expected {len(pre) + int(rec_off[hi])}")
-            finally:
-                os.close(fd)
+            end = _engine.drain_to_file(eng, output_file, len(pre) + int(rec_off[lo]))      # mapped file, or pwrite until done
+            if end != len(pre) + int(rec_off[hi]):
+                raise RuntimeError(f"rank {rank} wrote up to byte {end}, expected {len(pre) + int(rec_off[hi])}")
         except BaseException as e:  # noqa: BLE001
             err = e
         agree(err, "write shard")                     # doubles as the closing barrier
@@ -243,11 +224,8 @@ def run_multi_file_sharded(record, all_lists: Sequence, model_name: str, output_
             rel[1:] = np.cumsum(record_sizes(lengths[lo:hi], first_idx=lo))
 
             def sink(sa: int, sb: int, view: np.ndarray) -> None:
-                base = int(rel[sa])
-                for s in range(sa, sb):
-                    fname = filename_template.format(model=model_name, idx=lo + s)
-                    with open(os.path.join(output_dir, fname), "wb") as fh:
-                        fh.write(view[int(rel[s]) - base:int(rel[s + 1]) - base])
+                names = [filename_template.format(model=model_name, idx=lo + s) for s in range(sa, sb)]
+                _engine.write_record_files(output_dir, names, view, rel[sa:sb + 1] - int(rel[sa]))
 
             eng.drain(sink)
         except BaseException as e:  # noqa: BLE001

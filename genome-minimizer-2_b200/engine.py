@@ -8,8 +8,12 @@ image (`gm2_plan`, `gm2_emit_*`).  All compute is in libgm2.so; there is no CPU 
 """
 from __future__ import annotations
 
+import errno
+import mmap
 import os
+import stat
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -18,6 +22,7 @@ from . import _native
 from .genbank import read_genbank, sequence_bytes
 
 DEFAULT_CHUNK_BYTES = int(os.environ.get("GM2_CHUNK_BYTES", 256 << 20))
+FILE_RANGE_BYTES = int(os.environ.get("GM2_FILE_RANGE_BYTES", 1 << 30))    # progress granularity of drain_to_file
 SEQ_ID_PREFIX = "Minimized_E_coli_K12_MG1655_"      # the reference's literal (minimizer_2.py:476, :537)
 
 
@@ -268,6 +273,10 @@ class MinimizerEngine:
         self.ctx.emit_host(s0, s1, out)
         return out
 
+    def emit_into(self, s0: int, s1: int, out: np.ndarray) -> None:
+        """Records [s0,s1) into caller-owned host memory (pageable, pinned or a file mapping)."""
+        self.ctx.emit_host(s0, s1, out)
+
     def sequence(self, s: int) -> str:
         """Minimized sequence of sample s as str (what GenomeMinimiser.reduced_genome_str holds)."""
         off = self.ctx.record_offsets()
@@ -368,6 +377,107 @@ class MinimizerEngine:
         return total
 
 
+def drain_to_file(eng, target, file_pos: int, s0: int = 0, s1: Optional[int] = None,
+                  progress: Optional[Callable[[int, int], None]] = None) -> int:
+    """Records [s0,s1) into `target` (a path, or an open read-write descriptor that stays open) starting at
+    byte `file_pos`; returns the position after the last byte.
+
+    A regular file is grown to its final size and MAPPED, and `gm2_emit_host` produces straight into the
+    mapping: the expansion workers (two-bit transport) or the staging copy (image-bytes transport) write
+    the page-cache pages themselves, in parallel, with no intermediate buffer and no write() call —
+    into tmpfs that is 10x a single-threaded write().  Space is checked before anything is produced
+    (a full filesystem under a mapping is a SIGBUS, not an OSError).  Anything that is not a regular
+    file (/dev/null, a FIFO: written sequentially), a filesystem without shared mappings, or
+    GM2_FILE_SINK=write takes the portable form: pinned ping-pong buffers + (p)write until every byte is down.
+    `progress(sa, sb)` is called after each range of about GM2_FILE_RANGE_BYTES, in order."""
+    s1 = eng.S if s1 is None else s1
+    off = eng.ctx.record_offsets()
+    total = int(off[s1] - off[s0])
+    end_pos = file_pos + total
+    own_fd = not isinstance(target, int)
+    fd = os.open(target, os.O_RDWR) if own_fd else target
+    path = target if own_fd else f"<fd {fd}>"
+    try:
+        mm = None
+        regular = stat.S_ISREG(os.fstat(fd).st_mode)
+        if total > 0 and regular and os.environ.get("GM2_FILE_SINK", "map") != "write":
+            try:
+                if os.fstat(fd).st_size < end_pos:
+                    os.ftruncate(fd, end_pos)
+                vfs = os.fstatvfs(fd)
+                have = os.fstat(fd).st_blocks * 512
+                if vfs.f_bavail * vfs.f_frsize + have < end_pos:
+                    raise OSError(errno.ENOSPC, f"{path}: {end_pos:,} bytes needed, "
+                                                f"{vfs.f_bavail * vfs.f_frsize:,} free on the filesystem")
+                mm = mmap.mmap(fd, end_pos, access=mmap.ACCESS_WRITE)
+            except OSError as e:
+                if e.errno == errno.ENOSPC:
+                    raise
+                mm = None                                  # no shared mappings here: portable form below
+        if mm is not None:
+            view = np.frombuffer(mm, dtype=np.uint8)
+            try:
+                for a, b in eng.chunks(FILE_RANGE_BYTES, s0, s1):
+                    lo = file_pos + int(off[a] - off[s0])
+                    eng.emit_into(a, b, view[lo:lo + int(off[b] - off[a])])
+                    if progress is not None:
+                        progress(a, b)
+            finally:
+                del view
+                try:
+                    mm.close()
+                except BufferError:                        # an exception in flight still holds a slice
+                    pass
+            return end_pos
+        pos = [file_pos]
+
+        def sink(sa: int, sb: int, chunk: np.ndarray) -> None:
+            pos[0] = pwrite_all(fd, chunk, pos[0], positioned=regular)
+            if progress is not None:
+                progress(sa, sb)
+
+        eng.drain(sink, s0=s0, s1=s1)
+        if pos[0] != end_pos:
+            raise RuntimeError(f"wrote up to byte {pos[0]}, expected {end_pos}")
+        return end_pos
+    finally:
+        if own_fd:
+            os.close(fd)
+
+
+def pwrite_all(fd: int, view: np.ndarray, pos: int, positioned: bool = True) -> int:
+    """os.pwrite (os.write for pipes and devices) until every byte is down: a single write may be short
+    (ENOSPC part-way, a signal, or the kernel's 0x7ffff000 per-call cap).  Returns the position after the
+    last byte."""
+    mv = memoryview(view).cast("B")
+    while len(mv):
+        k = os.pwrite(fd, mv, pos) if positioned else os.write(fd, mv)
+        if k <= 0:
+            raise OSError(f"pwrite wrote {k} bytes at offset {pos} ({len(mv)} left)")
+        pos += k
+        mv = mv[k:]
+    return pos
+
+
+_FILE_WRITERS = max(1, min(8, (os.cpu_count() or 1)))
+
+
+def write_record_files(output_dir, names: Sequence[str], view: np.ndarray, rel_off: np.ndarray) -> None:
+    """One file per record of a drained chunk (`view`, record k at rel_off[k]:rel_off[k+1]), written by a few
+    threads at once: file creation and page-cache fills of ~MB files are per-file latency, not bandwidth
+    (write() releases the GIL).  Returns when every file is closed; the first error is re-raised."""
+    def one(k: int) -> None:
+        with open(os.path.join(output_dir, names[k]), "wb") as fh:
+            fh.write(view[int(rel_off[k]):int(rel_off[k + 1])])
+
+    if len(names) < 4 or _FILE_WRITERS == 1:
+        for k in range(len(names)):
+            one(k)
+        return
+    with ThreadPoolExecutor(max_workers=_FILE_WRITERS) as pool:
+        list(pool.map(one, range(len(names))))
+
+
 def shard_range(S: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous sample range of `rank` (rank order == file order)."""
     return (rank * S) // world, ((rank + 1) * S) // world
@@ -412,20 +522,23 @@ def run_single_file(record, all_lists, model_name: str, output_file: str, engine
     eng = engine or MinimizerEngine(record)
     try:
         lengths = eng.plan_lists(all_lists, first_idx=0)
-        with open(output_file, "wb") as out:
-            out.write((f"# Minimized genomes generated using model: {model_name}\n"
-                       f"# Total genomes: {n}\n"
-                       f"# Generated on: {np.datetime64('now')}\n").encode())
+        pre = (f"# Minimized genomes generated using model: {model_name}\n"
+               f"# Total genomes: {n}\n"
+               f"# Generated on: {np.datetime64('now')}\n").encode()
+        fd = os.open(output_file, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o666)
 
-            def sink(sa: int, sb: int, view: np.ndarray) -> None:
-                out.write(view)
-                for idx in range(sa, sb):                      # same lines, same order as the reference
-                    print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
-                    if _sampled(idx):
-                        L = int(lengths[idx])
-                        print(f"  → {L:,} bp ({_pct(G, L):.1f}% reduction)")
+        def progress(sa: int, sb: int) -> None:
+            for idx in range(sa, sb):                          # same lines, same order as the reference
+                print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
+                if _sampled(idx):
+                    L = int(lengths[idx])
+                    print(f"  → {L:,} bp ({_pct(G, L):.1f}% reduction)")
 
-            eng.drain(sink)
+        try:
+            pwrite_all(fd, np.frombuffer(pre, dtype=np.uint8), 0, positioned=False)
+            drain_to_file(eng, fd, len(pre), progress=progress)
+        finally:
+            os.close(fd)
     finally:
         if engine is None:
             eng.close()
@@ -450,11 +563,10 @@ def run_multi_file(record, all_lists, model_name: str, output_dir, filename_temp
 
         def sink(sa: int, sb: int, view: np.ndarray) -> None:
             base = int(rec_off[sa])
-            for idx in range(sa, sb):
+            names = [filename_template.format(model=model_name, idx=idx) for idx in range(sa, sb)]
+            write_record_files(output_dir, names, view, np.asarray(rec_off[sa:sb + 1]) - base)
+            for idx, fname in zip(range(sa, sb), names):       # the reference's lines, in its order
                 print(f"[{idx+1}/{n}] genes present: {len(all_lists[idx])}")
-                fname = filename_template.format(model=model_name, idx=idx)
-                with open(os.path.join(output_dir, fname), "wb") as fh:
-                    fh.write(view[int(rec_off[idx]) - base:int(rec_off[idx + 1]) - base])
                 if _sampled(idx):
                     L = int(lengths[idx])
                     print(f"  → saved {fname} | {L:,} bp ({_pct(G, L):.1f}% reduction)")
@@ -567,20 +679,23 @@ def run_single_file_from_probabilities(record, probs, col_names: Sequence[str], 
         lengths, counts = plan_from_probabilities(eng, space, probs, threshold)
         n = len(lengths)
         os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
-        with open(output_file, "wb") as out:
-            out.write((f"# Minimized genomes generated using model: {model_name}\n"
-                       f"# Total genomes: {n}\n"
-                       f"# Generated on: {np.datetime64('now')}\n").encode())
+        pre = (f"# Minimized genomes generated using model: {model_name}\n"
+               f"# Total genomes: {n}\n"
+               f"# Generated on: {np.datetime64('now')}\n").encode()
+        fd = os.open(output_file, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o666)
 
-            def sink(sa: int, sb: int, view: np.ndarray) -> None:
-                out.write(view)
-                for idx in range(sa, sb):
-                    print(f"[{idx+1}/{n}] genes present: {int(counts[idx])}")
-                    if _sampled(idx):
-                        L = int(lengths[idx])
-                        print(f"  → {L:,} bp ({_pct(G, L):.1f}% reduction)")
+        def progress(sa: int, sb: int) -> None:
+            for idx in range(sa, sb):
+                print(f"[{idx+1}/{n}] genes present: {int(counts[idx])}")
+                if _sampled(idx):
+                    L = int(lengths[idx])
+                    print(f"  → {L:,} bp ({_pct(G, L):.1f}% reduction)")
 
-            eng.drain(sink)
+        try:
+            pwrite_all(fd, np.frombuffer(pre, dtype=np.uint8), 0, positioned=False)
+            drain_to_file(eng, fd, len(pre), progress=progress)
+        finally:
+            os.close(fd)
     finally:
         if engine is None:
             eng.close()

@@ -41,10 +41,22 @@ class OracleEngine:
     def record_offsets(self):
         return np.concatenate([[0], np.cumsum([len(x) for x in self.images])]).astype(np.int64)
 
-    def drain(self, sink, max_bytes=0):
-        for a in range(0, len(self.images), 3):          # three records per chunk
-            b = min(a + 3, len(self.images))
+    @property
+    def S(self):
+        return len(self.images)
+
+    def chunks(self, max_bytes=0, s0=0, s1=None):
+        s1 = self.S if s1 is None else s1
+        return [(a, min(a + 3, s1)) for a in range(s0, s1, 3)]          # three records per chunk
+
+    def drain(self, sink, max_bytes=0, s0=0, s1=None):
+        for a, b in self.chunks(max_bytes, s0, s1):
             sink(a, b, np.frombuffer(b"".join(self.images[a:b]), dtype=np.uint8))
+
+    def emit_into(self, s0, s1, out):
+        data = np.frombuffer(b"".join(self.images[s0:s1]), dtype=np.uint8)
+        assert out.size == data.size
+        out[:] = data
 
     def close(self):
         pass

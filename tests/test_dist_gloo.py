@@ -29,9 +29,28 @@ class OracleEngine:
         self.images = [self.mo.record_bytes(first_idx + i, s.encode()) for i, s in enumerate(seqs)]
         return np.asarray([len(s) for s in seqs], dtype=np.int64)
 
-    def drain(self, sink, max_bytes=0):
-        for i, img in enumerate(self.images):                # one record per chunk: worst case for offsets
-            sink(i, i + 1, np.frombuffer(img, dtype=np.uint8))
+    # the surface engine.drain_to_file uses (mapped file: chunks + emit_into; portable form: drain)
+    @property
+    def S(self):
+        return len(self.images)
+
+    @property
+    def ctx(self):
+        return self
+
+    def record_offsets(self):
+        return np.concatenate([[0], np.cumsum([len(x) for x in self.images])]).astype(np.int64)
+
+    def chunks(self, max_bytes=0, s0=0, s1=None):
+        s1 = self.S if s1 is None else s1
+        return [(i, i + 1) for i in range(s0, s1)]           # one record per chunk: worst case for offsets
+
+    def emit_into(self, s0, s1, out):
+        out[:] = np.frombuffer(b"".join(self.images[s0:s1]), dtype=np.uint8)
+
+    def drain(self, sink, max_bytes=0, s0=0, s1=None):
+        for a, b in self.chunks(max_bytes, s0, s1):
+            sink(a, b, np.frombuffer(b"".join(self.images[a:b]), dtype=np.uint8))
 
 
 def _worker_multi(rank, world, port, case_name, out_dir, ret_path):

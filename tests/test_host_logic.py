@@ -2,6 +2,8 @@
 sharding, synthetic-data determinism.  CPU only."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pytest
 
@@ -95,3 +97,83 @@ def test_gene_list_file_round_trips_like_the_reference_reads_it(tmp_path):
     same = [["a", "b"], ["c", "d"]]
     np.save(p, np.array(same, dtype=object), allow_pickle=True)
     assert np.load(p, allow_pickle=True).tolist() == same
+
+
+# ----------------------------------------------------------------------------------------------
+# engine.drain_to_file: mapped file vs the portable (p)write form, through the engine double
+# ----------------------------------------------------------------------------------------------
+def _planned_double(name="rand_small_1"):
+    import tempfile
+    from conftest import load_golden
+    from oracle import genbank_reader
+    from engine_double import OracleEngine
+    case = load_golden(name)
+    with tempfile.NamedTemporaryFile("w", suffix=".gb", delete=False) as fh:
+        fh.write(case["genbank"])
+    rec = genbank_reader.read_genbank(fh.name)
+    os.unlink(fh.name)
+    eng = OracleEngine(rec)
+    eng.plan_lists(case["lists"])
+    return eng, b"".join(eng.images)
+
+
+@pytest.mark.parametrize("sink", ["map", "write"])
+def test_drain_to_file_forms_write_the_same_bytes(sink, tmp_path, monkeypatch):
+    from genome_minimizer_2_b200 import engine
+    monkeypatch.setenv("GM2_FILE_SINK", sink)
+    eng, image = _planned_double()
+    pre = b"# preamble\n"
+    path = tmp_path / "out.fasta"
+    path.write_bytes(pre)
+    seen = []
+    end = engine.drain_to_file(eng, str(path), len(pre), progress=lambda a, b: seen.append((a, b)))
+    assert end == len(pre) + len(image)
+    assert path.read_bytes() == pre + image
+    assert seen == eng.chunks() and seen[0][0] == 0 and seen[-1][1] == eng.S          # every range once, in order
+    # a sub-range at its own offset into a larger, pre-sized file (what a rank of the sharded form does)
+    off = eng.record_offsets()
+    big = tmp_path / "big.fasta"
+    with open(big, "wb") as fh:
+        fh.truncate(len(pre) + len(image))
+    a, b = 1, eng.S - 1
+    engine.drain_to_file(eng, str(big), len(pre) + int(off[a]), s0=a, s1=b)
+    got = big.read_bytes()
+    assert got[len(pre) + int(off[a]):len(pre) + int(off[b])] == image[int(off[a]):int(off[b])]
+    assert got[:len(pre) + int(off[a])].count(0) == len(pre) + int(off[a])            # nothing outside the range
+    assert got[len(pre) + int(off[b]):].count(0) == len(got) - len(pre) - int(off[b])
+
+
+def test_drain_to_file_takes_the_sequential_form_for_a_pipe(tmp_path):
+    from genome_minimizer_2_b200 import engine
+    eng, image = _planned_double()
+    r, w = os.pipe()
+    import threading
+    got = []
+    t = threading.Thread(target=lambda: got.append(os.fdopen(r, "rb").read()))
+    t.start()
+    try:
+        assert engine.drain_to_file(eng, w, 0) == len(image)
+    finally:
+        os.close(w)
+    t.join()
+    assert got[0] == image
+
+
+def test_drain_to_file_refuses_a_full_filesystem_before_producing(tmp_path, monkeypatch):
+    import errno
+    from genome_minimizer_2_b200 import engine
+    eng, image = _planned_double()
+    real = os.fstatvfs
+
+    class Full:
+        def __init__(self, v):
+            self.f_bavail, self.f_frsize = 0, v.f_frsize
+
+    monkeypatch.setattr(os, "fstatvfs", lambda fd: Full(real(fd)))
+    path = tmp_path / "o.fasta"
+    path.write_bytes(b"")
+    called = []
+    monkeypatch.setattr(type(eng), "emit_into", lambda self, a, b, out: called.append((a, b)))
+    with pytest.raises(OSError) as e:
+        engine.drain_to_file(eng, str(path), 0)
+    assert e.value.errno == errno.ENOSPC and not called
