@@ -828,6 +828,7 @@ def main():
     emit_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     clocks = sampler.stop() if rank == 0 else None
     emit_ctas = ctx.query(_native.Q_LAST_EMIT_CTAS)
+    tile_bytes_used = ctx.query(_native.Q_TILE_BYTES)
 
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -1047,7 +1048,7 @@ def main():
                    "output": f"device-resident FASTA image, {image_bytes/1e9:.2f} GB per GPU per step",
                    "l2": "no flush needed: each step writes an image >> 126 MB L2",
                    "sharding": "samples; reference replicated; all-gather of the step's per-sample lengths only",
-                   "tile_bytes": args.tile_bytes or 49152, "kept_bases_per_gpu": kept_bases,
+                   "tile_bytes": tile_bytes_used, "kept_bases_per_gpu": kept_bases,
                    "emit_ctas_per_sm": emit_ctas, "cpu_model": cpu_model(), "host_cores": os.cpu_count()},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_port_c": cpu_c, "verify": verify,

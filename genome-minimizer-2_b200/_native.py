@@ -19,7 +19,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 CFG_TILE_BYTES, CFG_EMIT_WARPS, CFG_EMIT_BATCH, CFG_PACKING, CFG_STORE_POLICY, CFG_RUN_TABLE, CFG_DEBUG, CFG_ORDER = 1, 2, 3, 4, 5, 6, 7, 8
 CFG_FLAT_RUN_BYTES, CFG_WIRE, CFG_HOST_THREADS, CFG_EMIT_OCCUPANCY, CFG_FLAT_MODE = 9, 10, 11, 12, 13
-Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS, Q_LAST_WIRE, Q_LAST_D2H_BYTES, Q_LAST_EMIT_CTAS, Q_LAST_FLAT_MODE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+Q_SM_COUNT, Q_LAUNCHES, Q_NUM_SEGMENTS, Q_NUM_TILES, Q_PACKING, Q_NUM_SLOTS, Q_KEEP_WORDS, Q_LAST_WIRE, Q_LAST_D2H_BYTES, Q_LAST_EMIT_CTAS, Q_LAST_FLAT_MODE, Q_TILE_BYTES = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
 
 _c = ctypes
 _P = _c.c_void_p

@@ -62,7 +62,8 @@ struct gm2_ctx {
     uint64_t launches = 0;
 
     // configuration
-    int tile_bytes = 49152;        // best measured (profiles/r01_emit_experiments.md): 3 CTAs of 8 warps per SM
+    int tile_bytes = 49152;        // bases staged per CTA: what gm2_set_reference last used (configured or chosen)
+    int tile_bytes_cfg = 0;        // GM2_CFG_TILE_BYTES; 0 = chosen from the reference's gene density (auto_tile_bytes)
     int emit_warps = 8;
     int emit_batch = 0;
     int packing_req = 0;
@@ -281,9 +282,9 @@ GM2_API int gm2_configure(gm2_ctx* c, int key, int64_t value) {
     switch (key) {
     case GM2_CFG_TILE_BYTES:
         if (c->have_ref) return fail(c, GM2_ERR_STATE, "GM2_CFG_TILE_BYTES must be set before gm2_set_reference");
-        if (value < 4096 || value > 196608 || (value % 4096) != 0)
-            return fail(c, GM2_ERR_INVALID, "tile bytes must be a multiple of 4096 in [4096, 196608]");
-        c->tile_bytes = (int)value; return GM2_OK;
+        if (value != 0 && (value < 4096 || value > 196608 || (value % 4096) != 0))
+            return fail(c, GM2_ERR_INVALID, "tile bytes must be 0 (auto) or a multiple of 4096 in [4096, 196608]");
+        c->tile_bytes_cfg = (int)value; if (value) c->tile_bytes = (int)value; return GM2_OK;
     case GM2_CFG_EMIT_WARPS:
         if (value < 1 || value > 8) return fail(c, GM2_ERR_INVALID, "emit warps must be in 1..8");
         c->emit_warps = (int)value; return GM2_OK;
@@ -339,6 +340,7 @@ GM2_API int gm2_query(const gm2_ctx* c, int key, int64_t* out) {
     case GM2_Q_LAST_D2H_BYTES: *out = c->last_d2h_bytes; return GM2_OK;
     case GM2_Q_LAST_EMIT_CTAS: *out = c->last_emit_ctas; return GM2_OK;
     case GM2_Q_LAST_FLAT_MODE: *out = c->last_flat_mode; return GM2_OK;
+    case GM2_Q_TILE_BYTES: *out = c->tile_bytes; return GM2_OK;
     default: return GM2_ERR_INVALID;
     }
 }
@@ -365,6 +367,19 @@ GM2_API int gm2_set_header_prefix(gm2_ctx* c, const char* prefix) {
     return GM2_OK;
 }
 
+// Tile size when none is configured.  k_emit's short-run form handles the kept runs of a (sample, tile) visit 32 at
+// a time, lane <-> run, and a visit meets about one run per gene of the tile when few genes are kept; so the
+// tile is sized for ~34 genes (the 33rd run costs a second, nearly empty pass over the lanes), rounded to 4 KB
+// and clamped to [24 KB, 48 KB].  Measured on both benchmark shapes (profiles/r02_emit_low_retention.md): 36 KB
+// for 4,400 genes on 4.64 Mbp, 40 KB for 10,000 genes on 12 Mbp, +6-8 % at 10-20 % gene retention against a fixed
+// 48 KB; from 50 % retention up every size in that range writes at the same rate.
+static int auto_tile_bytes(int64_t G, int64_t genes) {
+    if (genes <= 0 || G <= 0) return 49152;
+    const int64_t want = 34 * G / genes;
+    const int64_t t = ((want + 2048) / 4096) * 4096;
+    return (int)std::min<int64_t>(std::max<int64_t>(t, 24576), 49152);
+}
+
 GM2_API int gm2_set_reference(gm2_ctx* c, const uint8_t* seq, int64_t G,
                               const int64_t* gs, const int64_t* ge, int32_t F)
 try {
@@ -373,6 +388,11 @@ try {
         return fail(c, GM2_ERR_INVALID, "gm2_set_reference: bad arguments");
     if (G > (int64_t)0x7fff0000) return fail(c, GM2_ERR_INVALID, "gm2_set_reference: G must be below 2^31 - 65536");
     CU(c, cudaSetDevice(c->device));
+    if (c->tile_bytes_cfg == 0) {
+        int64_t genes = 0;
+        for (int32_t g = 0; g < F; ++g) genes += std::min(std::max<int64_t>(ge[g], 0), G) > std::min(std::max<int64_t>(gs[g], 0), G);
+        c->tile_bytes = auto_tile_bytes(G, genes);
+    }
     const int64_t T = c->tile_bytes;
     const int ntiles = (int)((G + T - 1) / T);
 
@@ -806,36 +826,39 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     p.tile_bytes = c->tile_bytes; p.ntiles = c->ntiles; p.SW = c->SW; p.batch = (int)batch; p.nbatch = (int)nbatch;
     p.slot_cap = c->max_tile_slots <= 4096 ? c->max_tile_slots : 0;     // else: slot tables read from global
     p.prefix = c->prefix; p.debug = c->debug; p.order = c->order; p.flat_run_bytes = c->flat_run_bytes;
-    // Shared memory and registers decide how many CTAs an SM holds: up to 56 KB and the 62-register
-    // build -> 4 CTAs (32 warps), else the 72-register build -> 3 CTAs.  Measured on the K-12 shape
-    // (profiles/r01_emit_experiments.md, "Occupancy vs retention"): where the kernel is
-    // instruction/latency-bound (short runs, low retention) 4 CTAs are 7-12 % faster; where it is
-    // write-bound (kept fraction above ~0.45) the extra concurrent write streams cost 2-3 %.  With the
-    // default 48 KB tile the only difference between the two is the per-warp run table (32 instead
-    // of 64 entries), so the choice is made here, per launch, from the kept fraction of the latest
-    // plan known to the host — same plan, same bytes either way.
+    // Two builds of k_emit: 64 registers (4 CTAs of 256 threads per SM, needs <= 56 KB of shared memory per CTA:
+    // with the default 48 KB tile that means a 32-entry run table) and 72 registers (3 CTAs).  Same plan, same
+    // bytes either way, so the choice is made here, per launch, from the kept fraction of the latest plan known
+    // to the host.
     auto smem_for = [&](int rt) {
         return 32 + (size_t)p.tile_smem_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (rt + 2) * 24;
     };
     const size_t dense_limit = 56 * 1024;
     poll_kept_frac(c);
     int rt_cap = c->rt_cap;
+    // Launch form, re-measured with the bitmap-indexed short-run form and the gene-density tile
+    // (profiles/r02_emit_low_retention.md): with tiles of 28-48 KB the 72-register build is the faster one at
+    // every retention (fewer instructions; at low retention the L1 data pipe — shared loads + global stores —
+    // is the limit, not latency, and above ~45 % kept the kernel is write-bound and 3 CTAs are 2 % faster).
+    // Only small tiles (<= 24 KB: gene-dense references) below ~43 % kept gain from the fourth CTA (+5-7 %).
     const bool want4 = c->emit_occupancy == 4 ||
-                       (c->emit_occupancy == 0 && c->kept_frac >= 0.0 && c->kept_frac < 0.43);
+                       (c->emit_occupancy == 0 && c->tile_bytes <= 24576 && c->kept_frac >= 0.0 && c->kept_frac < 0.43);
     if (want4 && smem_for(rt_cap) > dense_limit && smem_for(32) <= dense_limit) rt_cap = 32;
     p.rt_cap = rt_cap;
     // visit_flat keeps packed 4-byte entries in the same per-warp region ((rt_cap + 2) * 24 bytes): table A and the
-    // event table with 2 * rt_cap + 2 entries each, the rest (2 * rt_cap + 8 words) is its vector bitmap
-    // Which short-run form (measured, profiles/r02_emit_low_retention.md): the bitmap-indexed whole-visit form wins
-    // where nearly every run is an intergenic gap (gene retention ~10 %: kept fraction of the bases below ~0.26),
-    // the per-batch cursor form from ~20 % up, where long runs inside short-run tiles go to the run-by-run stream.
-    const bool want2 = c->flat_mode == 2 || (c->flat_mode == 0 && c->kept_frac >= 0.0 && c->kept_frac < 0.26);
+    // event table with 2 * rt_cap + 2 entries each, the rest (2 * rt_cap + 8 words) holds rt_cap + 4 bitmap entries
+    // {event word, skip word}, one per 512-byte output row; phase I reads pairs of entries one pair ahead, so
+    // the last five stay spare.
+    // Short-run form: the bitmap-indexed whole-visit form (2) is at least as fast as the per-batch cursor form (1)
+    // at every retention measured (0.1 ... 0.9, both genome shapes) and 15-25 % faster below 30 %, so auto means 2
+    // wherever it applies (one byte per base, tile <= 60 KB); 1 stays selectable for A/B runs.
+    const bool want2 = c->flat_mode == 2 || c->flat_mode == 0;
     const bool flat2 = want2 && !two_bit && c->tile_bytes <= FLAT_MAX_TILE;
     p.flat_cap = flat2 ? 2 * rt_cap : 0;
-    p.flat_bm_words = flat2 ? 2 * rt_cap + 8 : 0;
+    p.flat_bm_words = flat2 ? rt_cap - 1 : 0;
     const size_t sm = smem_for(rt_cap);
     if (sm > 227 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_emit: shared memory budget exceeded; lower tile bytes / emit warps");
-    const bool dense = sm <= dense_limit;
+    const bool dense = want4 && sm <= dense_limit;         // which build: 64 registers (4 CTAs of 256 threads) or 72 (3)
     c->last_emit_ctas = dense ? 4 : 3;
     c->last_flat_mode = flat2 ? 2 : 1;
     void (*kern)(const EmitParams);

@@ -384,13 +384,16 @@ __device__ __forceinline__ void emit_runs_flat(uint32_t tile_a, uint32_t rt_a, i
 //              byte; everything fits 16 bits (tile <= 60 KB), so a run is ONE packed word
 //              A[r] = R_r | S_r << 16  (S = source offset in the staged tile), A[nr] = R_end.
 //   events     an "event" is a vector in which at least one run starts.  One pass, lane <-> run,
-//              writes EV[e] = A[last run starting in that vector] (ballot + popc ranks) and sets bit
-//              (R >> 4) of a per-warp bitmap (shared-memory atomic OR).
-//   phase I    row i, lane L: m = BM[i] (broadcast); the vector's run is EV[base + popc(m & lt) - 1
-//              + bit] — no search; it is an interior vector unless its bit is set and the event's run
-//              does not start exactly on it.  Interior: two aligned LDS.128, word select, funnel
-//              shift, one STG.128.  A row whose word is 0 lies inside ONE run: warp-uniform phase, no
-//              selects (copy_vectors).
+//              writes EV[e] = tile address + S - R of the LAST run starting in that vector (ballot + popc
+//              ranks), i.e. "source address of output byte 0 if it belonged to that run", and sets two
+//              bits per vector in a per-warp bitmap pair (shared-memory atomic OR): `event` (a run starts
+//              in it) and `skip` (a run starts inside it, not on its first byte: phase B's vector).  The
+//              skip word also masks everything from the visit's last partial vector on, so phase I has
+//              no range checks at all.
+//   phase I    row i (512 output bytes), lane L: {event, skip} = BM[i] (one broadcast 64-bit load); the
+//              vector's source is EV[base + popc(event & le) - 1] + pos — no search, no compare; unless
+//              its skip bit is set the lane copies it: two aligned LDS.128, word select, funnel shift,
+//              one STG.128.  ~40 warp instructions per row whatever the number of runs in it.
 //   phase B    same pass as the events, lane <-> run: the first run starting in a vector owns it; up to
 //              three sources (tail of the previous run, one or two starts) are fetched as unaligned
 //              16-byte windows and merged under byte masks; more than three
@@ -407,6 +410,19 @@ __device__ __forceinline__ uint32_t tb_load(uint32_t a) {                 // per
 }
 __device__ __forceinline__ void tb_store(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 tb_load2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 tb_load4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tb_store2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tb_or(uint32_t a, uint32_t v) {
     asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
@@ -452,12 +468,49 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
     uint8_t* base16 = out0 - o;
     asm volatile("" : "+l"(base16), "+r"(tile_a), "+r"(lt_mask));       // keep these in registers (no re-derivation per row)
     const int r_end = o + bytes;
-    const int nbm = ((r_end - 1) >> 9) + 1;                          // rows (= bitmap words) the visit touches
-    for (int i = lane; i < nbm; i += 32) tb_store(bm_a + 4u * i, 0u);
+    const int nbm = ((r_end - 1) >> 9) + 1;                          // rows (= bitmap entries) the visit touches
+    const int vl = r_end >> 4;                                       // first vector that is not whole inside the visit
+    // bitmap entry i = {event bits, skip bits} of row i; the skip words mask everything from vector vl on,
+    // including the whole entry after the last row (phase I works on pairs of rows)
+    for (int i = lane; i <= nbm; i += 32)
+        tb_store2(bm_a + 8u * i, 0u, i > (vl >> 5) ? 0xffffffffu : i == (vl >> 5) ? 0xffffffffu << (vl & 31) : 0u);
 
     // ---- table A: one packed word per kept run
     int nr = 0;
-    {
+    if (nwords <= 4) {
+        // lane <-> four consecutive slots (a tile of the usual shapes has 64-128 slots): the kept lengths and the
+        // run starts of the whole tile go through ONE warp scan, packed {bytes : 20 | starts : 12} — a lane holds
+        // at most two run starts (starts are never adjacent).  Lanes past the tile's slots see kept bits 0 and
+        // read table entries that are never used.
+        const uint32_t wsrc = __shfl_sync(FULL_MASK, words, lane >> 3);           // word c sits in lane c
+        const uint32_t nib = (wsrc >> (4 * (lane & 7))) & 0xfu;
+        const uint4 l4 = lds128(len_a + 16u * (uint32_t)lane);
+        const uint4 s4 = lds128(src_a + 16u * (uint32_t)lane);
+        uint32_t up = __shfl_up_sync(FULL_MASK, nib, 1);
+        if (lane == 0) up = 0u;
+        const uint32_t st = nib & ~((nib << 1) | (up >> 3));
+        const int p1 = (nib & 1u) ? (int)l4.x : 0;                                // kept bytes before slot 1, 2, 3 of this lane
+        const int p2 = p1 + ((nib & 2u) ? (int)l4.y : 0);
+        const int p3 = p2 + ((nib & 4u) ? (int)l4.z : 0);
+        const int tot = p3 + ((nib & 8u) ? (int)l4.w : 0);
+        const int mine = tot | (__popc(st) << 20);
+        const int incl = warp_incl_scan(mine, lane);
+        const int excl = incl - mine;
+        nr = (int)((uint32_t)__shfl_sync(FULL_MASK, incl, 31) >> 20);
+        if (st) {
+            const int q = o + (excl & 0xfffff);
+            const uint32_t ra = a_a + 4u * ((uint32_t)excl >> 20);
+            const int j0 = __ffs((int)st) - 1;                                    // first start: slot 0..3
+            const int pj = j0 == 0 ? 0 : j0 == 1 ? p1 : j0 == 2 ? p2 : p3;
+            const uint32_t sj = j0 == 0 ? s4.x : j0 == 1 ? s4.y : j0 == 2 ? s4.z : s4.w;
+            tb_store(ra, (uint32_t)(q + pj) | (sj << 16));
+            if (st & (st - 1u)) {                                                 // a second start: slot 2 or 3
+                const bool at3 = (st & 8u) != 0u;
+                tb_store(ra + 4u, (uint32_t)(q + (at3 ? p3 : p2)) | ((at3 ? s4.w : s4.z) << 16));
+            }
+        }
+        if (lane == 0) tb_store(a_a + 4u * nr, (uint32_t)r_end);
+    } else {
         int q = o;
         uint32_t carry = 0u;
         for (int c = 0; c < nwords; ++c) {
@@ -525,7 +578,9 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
                 }
                 st128<POLICY>(base16 + p0, ov);
             }
-            if (last) tb_or(bm_a + 4u * (uint32_t)(v >> 5), 1u << (v & 31));
+            if (last) tb_or(bm_a + 8u * (uint32_t)(v >> 5), 1u << (v & 31));
+            if (R & 15) tb_or(bm_a + 8u * (uint32_t)(v >> 5) + 4u, 1u << (v & 31));
+            x = tile_a + (x >> 16) - (uint32_t)R;                                 // source address of output byte 0 in run r's frame
         }
         const uint32_t bal = __ballot_sync(FULL_MASK, last);
         if (last) tb_store(ev_a + 4u * (ne + __popc(bal & lt_mask)), x);
@@ -533,51 +588,41 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
     }
     __syncwarp();
 
-    // ---- phase I: interior vectors, row by row.  The next row's bitmap word and event entry are fetched
-    // before the current row is copied (the table reads are ordered asm statements: nothing else overlaps
-    // their latency with the copy).
+    // ---- phase I: interior vectors, two rows (1 KB of output) per step.  Nothing here branches on data: the
+    // two rows' bitmap entries arrive in one 128-bit load, fetched one step ahead (the table reads are ordered
+    // asm statements: nothing else overlaps their latency); both source windows are loaded unconditionally
+    // (a skipped lane reads valid shared memory near its run and drops it) and only the store is predicated,
+    // so the two rows' instruction streams interleave.  Entries past the last row are skip-all / never used.
+    // (Measured and dropped: issuing the next step's event look-ups before this step's select/shift/store,
+    // -2.5 % — at this point the L1 data pipe, shared loads + global stores, is ~80 % busy, not latency.)
     {
-        int base = 0, i = 0;
-        uint32_t m = tb_load(bm_a);                                               // row 0 always holds event 0 (bit 0)
-        uint32_t e = tb_load(ev_a + 4u * (uint32_t)(__popc(m & lt_mask) - 1 + (int)((m >> lane) & 1u)));
+        uint32_t le_mask = lt_mask | (1u << lane), lane_bit = 1u << lane;
+        asm volatile("" : "+r"(le_mask), "+r"(lane_bit));
+        uint32_t evp = ev_a - 4u;                                                 // &EV[events of earlier rows - 1]
+        uint32_t pa = (uint32_t)(lane << 4);                                      // this lane's output offset
+        uint8_t* d = base16 + (lane << 4);
+        uint32_t bmp = bm_a;
+        auto rows2 = [&](const uint4& mk) {
+            const int n0 = __popc(mk.x);
+            const uint32_t ea0 = tb_load(evp + 4u * (uint32_t)__popc(mk.x & le_mask));
+            const uint32_t ea1 = tb_load(evp + 4u * (uint32_t)(n0 + __popc(mk.z & le_mask)));
+            evp += 4u * (uint32_t)(n0 + __popc(mk.z));
+            const uint4 v0 = lds_unaligned16(ea0 + pa);
+            const uint4 v1 = lds_unaligned16(ea1 + pa + 512u);
+            if ((mk.y & lane_bit) == 0u) st128<POLICY>(d, v0);
+            if ((mk.w & lane_bit) == 0u) st128<POLICY>(d + 512, v1);
+            pa += 1024u; d += 1024;
+        };
+        uint4 mk = tb_load4(bmp);                                                 // row 0 always holds event 0 (bit 0)
 #pragma unroll 1
-        while (i < nbm) {
-            if (m == 0u && (i << 9) + 512 <= r_end) {
-                // rows i .. i+k-1 lie inside the run of event base-1: warp-uniform source phase, no word select
-                int k = 1;
-                while (i + k < nbm && ((i + k) << 9) + 512 <= r_end && tb_load(bm_a + 4u * (uint32_t)(i + k)) == 0u) ++k;
-                const uint32_t a = tile_a + (e >> 16) + (uint32_t)((i << 9) + (lane << 4) - (int)(e & 0xffffu));
-                const int mis = (int)(a & 15u);                                   // same for every lane: positions are multiples of 16
-                uint8_t* d = base16 + (i << 9) + (lane << 4);
-                const int nb = k << 5, sh = (mis & 3) * 8;
-                const uint32_t qa = a - (uint32_t)mis;
-                if (mis == 0) {
-                    uint32_t q = qa;
-#pragma unroll 1
-                    for (int v = lane; v < nb; v += 32, q += 512, d += 512) st128<POLICY>(d, lds128(q));
-                } else {
-                    switch (mis >> 2) {
-                    case 0:  copy_vectors<POLICY, 0>(qa, d, nb, sh, lane); break;
-                    case 1:  copy_vectors<POLICY, 1>(qa, d, nb, sh, lane); break;
-                    case 2:  copy_vectors<POLICY, 2>(qa, d, nb, sh, lane); break;
-                    default: copy_vectors<POLICY, 3>(qa, d, nb, sh, lane); break;
-                    }
-                }
-                i += k;
-                if (i < nbm) {
-                    m = tb_load(bm_a + 4u * (uint32_t)i);
-                    e = tb_load(ev_a + 4u * (uint32_t)(base + __popc(m & lt_mask) - 1 + (int)((m >> lane) & 1u)));
-                }
-                continue;
-            }
-            const int base_n = base + __popc(m);
-            const uint32_t m_n = i + 1 < nbm ? tb_load(bm_a + 4u * (uint32_t)(i + 1)) : 0u;
-            const uint32_t e_n = tb_load(ev_a + 4u * (uint32_t)(base_n + __popc(m_n & lt_mask) - 1 + (int)((m_n >> lane) & 1u)));
-            const int pos = (i << 9) + (lane << 4);
-            const int R = (int)(e & 0xffffu);
-            if (pos >= o && pos + 16 <= r_end && (((m >> lane) & 1u) == 0u || R == pos))
-                st128<POLICY>(base16 + pos, lds_unaligned16(tile_a + (e >> 16) + (uint32_t)(pos - R)));
-            m = m_n; e = e_n; base = base_n; ++i;
+        for (int i = 0; ; i += 4) {
+            const uint4 nx = tb_load4(bmp + 16u);
+            rows2(mk);
+            if (i + 2 >= nbm) break;
+            mk = tb_load4(bmp + 32u);
+            bmp += 32u;
+            rows2(nx);
+            if (i + 4 >= nbm) break;
         }
     }
 

@@ -47,7 +47,8 @@ extern "C" {
 #define GM2_ERR_UNSUPPORTED -6 /* input outside the subset this entry point handles (caller has a slower general path) */
 
 /* gm2_configure keys */
-#define GM2_CFG_TILE_BYTES    1  /* reference bases staged per CTA (multiple of 4096; before set_reference) */
+#define GM2_CFG_TILE_BYTES    1  /* reference bases staged per CTA (multiple of 4096, or 0 = chosen from the gene
+                                   density at gm2_set_reference, the default; before set_reference) */
 #define GM2_CFG_EMIT_WARPS    2  /* warps per emit CTA (1..8)                                */
 #define GM2_CFG_EMIT_BATCH    3  /* samples per emit CTA; 0 = choose from S and the SM count */
 #define GM2_CFG_PACKING       4  /* 0 auto (= byte, the measured-faster form), 1 byte/base, 2 two-bit (ACGT-only; before set_reference) */
@@ -62,12 +63,13 @@ extern "C" {
                                     LOCAL_WORLD_SIZE says several processes share the host), 1 image bytes over PCIe,
                                     2 two bits per base over PCIe + expansion by host threads (error if not ACGT-only) */
 #define GM2_CFG_HOST_THREADS  11 /* host threads for that expansion; 0 = hardware threads / LOCAL_WORLD_SIZE */
-#define GM2_CFG_EMIT_OCCUPANCY 12 /* k_emit CTAs per SM: 0 auto (4 when the latest plan kept less than ~43 % of the bases —
-                                   * short kept runs, instruction-bound — else 3), 3, or 4 (when the shared memory fits) */
-#define GM2_CFG_FLAT_MODE     13 /* form of that short-run path: 2 = whole visit, vector -> run through a per-warp bitmap
-                                  * of run starts (no search), boundary vectors merged from <= 3 windows; 1 = per flushed
-                                  * batch, private run cursor per lane; 0 (default) = 2 when the latest plan kept less than
-                                  * ~26 % of the bases (nearly every run an intergenic gap), else 1 */
+#define GM2_CFG_EMIT_OCCUPANCY 12 /* k_emit build / CTAs per SM: 0 auto (the 72-register build, 3 CTAs; the 64-register
+                                   * build, 4 CTAs, only for tiles <= 24 KB when the latest plan kept less than ~43 % of
+                                   * the bases), 3, or 4 (when the shared memory fits) */
+#define GM2_CFG_FLAT_MODE     13 /* form of that short-run path: 2 = whole visit, vector -> run through a per-warp pair of
+                                  * bitmaps (run starts / boundary vectors: no search, no compare), boundary vectors
+                                  * merged from <= 3 windows; 1 = per flushed batch, private run cursor per lane;
+                                  * 0 (default) = 2 wherever it applies (one byte per base, tile <= 60 KB) */
 #define GM2_CFG_DEBUG         7  /* timing knock-outs (WRONG output); only effective in -DGM2_EMIT_DEBUG builds */
 
 /* gm2_query keys */
@@ -82,6 +84,7 @@ extern "C" {
 #define GM2_Q_LAST_D2H_BYTES  9  /* device->host bytes the last gm2_emit_host moved  */
 #define GM2_Q_LAST_EMIT_CTAS  10 /* CTAs per SM the last k_emit launch was configured for (3 or 4) */
 #define GM2_Q_LAST_FLAT_MODE  11 /* short-run form of the last k_emit launch (1 or 2, see GM2_CFG_FLAT_MODE) */
+#define GM2_Q_TILE_BYTES      12 /* tile size gm2_set_reference used (configured or chosen)               */
 
 typedef struct gm2_ctx gm2_ctx;
 

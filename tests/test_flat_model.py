@@ -32,7 +32,11 @@ def model_visit_flat(tile: np.ndarray, runs, o: int):
         q += ln
     A.append(r_end)
     nbm = ((r_end - 1) >> 9) + 1
-    BM = [0] * nbm
+    vl = r_end >> 4
+    # entry i = [event word, skip word] of row i; entries past the last row are skip-all (phase I works on
+    # pairs of rows and reads one pair ahead)
+    BM = [[0, 0xFFFFFFFF if i > (vl >> 5) else ((0xFFFFFFFF << (vl & 31)) & 0xFFFFFFFF) if i == (vl >> 5) else 0]
+          for i in range(nbm + 1)]
     EV = []
 
     def lds_unaligned16(a: int):                      # a may be negative by < 16 (front pad) or run past the tile (back pad)
@@ -99,7 +103,10 @@ def model_visit_flat(tile: np.ndarray, runs, o: int):
                             ov.append(int(tile[(xc >> 16) + p0 + j - (xc & 0xFFFF)]))
                     st128(p0, ov)
                 if last:
-                    BM[v >> 5] |= 1 << (v & 31)
+                    BM[v >> 5][0] |= 1 << (v & 31)
+                if R & 15:
+                    BM[v >> 5][1] |= 1 << (v & 31)
+                x = (x >> 16) - R                      # source offset of output byte 0 in run r's frame (kernel: + tile_a)
             lasts.append((last, x))
         bal = sum(1 << i for i, (l, _) in enumerate(lasts) if l)
         for lane, (l, x) in enumerate(lasts):
@@ -111,38 +118,38 @@ def model_visit_flat(tile: np.ndarray, runs, o: int):
         ne += popc(bal)
     assert all(e is not None for e in EV) and len(EV) == ne
 
-    # ---- phase I (same control flow as the kernel: batched uniform rows, next row's word / event fetched early)
-    lt = [(1 << lane) - 1 for lane in range(32)]
-    base, i = 0, 0
-    m = BM[0]
-    e = [EV[popc(m & lt[lane]) - 1 + ((m >> lane) & 1)] for lane in range(32)]
-    while i < nbm:
-        if m == 0 and (i << 9) + 512 <= r_end:
-            k = 1
-            while i + k < nbm and ((i + k) << 9) + 512 <= r_end and BM[i + k] == 0:
-                k += 1
-            assert len(set(e)) == 1
-            for lane in range(32):
-                a = (e[lane] >> 16) + (i << 9) + (lane << 4) - (e[lane] & 0xFFFF)
-                for v in range(k):
-                    st128((i << 9) + (lane << 4) + 512 * v, lds_unaligned16(a + 512 * v))
-            i += k
-            if i < nbm:
-                m = BM[i]
-                e = [EV[base + popc(m & lt[lane]) - 1 + ((m >> lane) & 1)] for lane in range(32)]
-            continue
-        base_n = base + popc(m)
-        m_n = BM[i + 1] if i + 1 < nbm else 0
-        e_n = [EV[base_n + popc(m_n & lt[lane]) - 1 + ((m_n >> lane) & 1)] for lane in range(32)]
+    # ---- phase I (same control flow as the kernel: two rows per step, unconditional source windows,
+    # predicated stores, entries fetched one pair ahead)
+    le = [(2 << lane) - 1 for lane in range(32)]
+    evp = -1                                                 # index of EV[events of earlier rows - 1]
+    pa = [lane << 4 for lane in range(32)]
+
+    def rows2(mk):
+        nonlocal evp
+        ev0, sk0, ev1, sk1 = mk
+        n0 = popc(ev0)
         for lane in range(32):
-            pos = (i << 9) + (lane << 4)
-            R = e[lane] & 0xFFFF
-            if pos >= o and pos + 16 <= r_end and (((m >> lane) & 1) == 0 or R == pos):
-                st128(pos, lds_unaligned16((e[lane] >> 16) + pos - R))
-        m, e, base, i = m_n, e_n, base_n, i + 1
+            ea0 = EV[evp + popc(ev0 & le[lane])]
+            ea1 = EV[evp + n0 + popc(ev1 & le[lane])]
+            v0 = lds_unaligned16(ea0 + pa[lane])
+            v1 = lds_unaligned16(ea1 + pa[lane] + 512)
+            if not (sk0 >> lane) & 1:
+                st128(pa[lane], v0)
+            if not (sk1 >> lane) & 1:
+                st128(pa[lane] + 512, v1)
+            pa[lane] += 1024
+        evp += n0 + popc(ev1)
+
+    def load4(i):
+        assert i + 1 < len(BM)
+        return BM[i][0], BM[i][1], BM[i + 1][0], BM[i + 1][1]
+
+    # the kernel looks one pair ahead (events) and two pairs ahead (bitmap entries); what it reads there is
+    # never used, but it must stay inside the per-warp region: entries up to nbm + 4
+    for i in range(0, nbm, 2):
+        rows2(load4(i))
 
     # ---- phase E
-    vl = r_end >> 4
     for lane in range(32):
         pos = -1
         if lane < 16:
@@ -227,3 +234,74 @@ def test_visit_flat_model_edge_shapes():
         got, w, _ = model_visit_flat(tile, runs, o)
         assert np.array_equal(w, np.ones_like(w)), (runs[:4], o)
         assert np.array_equal(got, reference_gather(tile, runs)), (runs[:4], o)
+
+
+# ----------------------------------------------------------------------------------------------
+# table A of visit_flat for tiles of at most 128 slots: lane <-> four consecutive slots, one warp scan
+# over {kept bytes : 20 bits | run starts : 12 bits}, at most two run starts per lane
+# ----------------------------------------------------------------------------------------------
+def model_table_a_four_slots(lens, srcs, words, o):
+    """lens/srcs: 128 slot entries (entries past the tile's slots hold garbage), words: 4 kept-bit words."""
+    nib, st, p, tot, mine = [0] * 32, [0] * 32, [None] * 32, [0] * 32, [0] * 32
+    for lane in range(32):
+        nib[lane] = (words[lane >> 3] >> (4 * (lane & 7))) & 0xF
+    for lane in range(32):
+        up = nib[lane - 1] if lane else 0
+        st[lane] = nib[lane] & ~((nib[lane] << 1) | (up >> 3)) & 0xFFFFFFFF
+        l4 = lens[4 * lane:4 * lane + 4]
+        p1 = l4[0] if nib[lane] & 1 else 0
+        p2 = p1 + (l4[1] if nib[lane] & 2 else 0)
+        p3 = p2 + (l4[2] if nib[lane] & 4 else 0)
+        tot[lane] = p3 + (l4[3] if nib[lane] & 8 else 0)
+        p[lane] = (0, p1, p2, p3)
+        assert st[lane] < 16 and popc(st[lane]) <= 2
+        mine[lane] = tot[lane] | (popc(st[lane]) << 20)
+    incl, acc = [], 0
+    for lane in range(32):
+        acc += mine[lane]
+        incl.append(acc)
+    assert (incl[31] & 0xFFFFF) < (1 << 20)
+    nr = incl[31] >> 20
+    A = [None] * (nr + 1)
+    for lane in range(32):
+        if st[lane]:
+            excl = incl[lane] - mine[lane]
+            q = o + (excl & 0xFFFFF)
+            ra = excl >> 20
+            j0 = (st[lane] & -st[lane]).bit_length() - 1
+            A[ra] = (q + p[lane][j0]) | (srcs[4 * lane + j0] << 16)
+            if st[lane] & (st[lane] - 1):
+                at3 = bool(st[lane] & 8)
+                A[ra + 1] = (q + (p[lane][3] if at3 else p[lane][2])) | (srcs[4 * lane + (3 if at3 else 2)] << 16)
+    A[nr] = o + (incl[31] & 0xFFFFF)
+    return A
+
+
+def test_table_a_four_slot_form_equals_the_word_by_word_form():
+    rng = np.random.default_rng(11)
+    for trial in range(400):
+        nslots = int(rng.choice([32, 64, 96, 128]))
+        lens = rng.integers(0, 700, 128).tolist()
+        srcs = np.concatenate([[0], np.cumsum(lens[:-1])]).tolist()
+        dens = float(rng.choice([0.05, 0.3, 0.5, 0.9, 1.0]))
+        bits = (rng.random(128) < dens).astype(int)
+        bits[nslots:] = 0                                   # words past the tile are 0
+        for i in range(nslots, 128):
+            lens[i] = int(rng.integers(0, 1 << 20))         # garbage the kernel may read and must ignore
+        words = [sum(int(bits[32 * c + i]) << i for i in range(32)) for c in range(4)]
+        o = int(rng.integers(0, 16))
+        # word-by-word form (the kernel's general path)
+        A, q, carry = [], o, 0
+        for c in range(4):
+            w = words[c]
+            starts = w & ~((w << 1) | carry) & 0xFFFFFFFF
+            carry = w >> 31
+            for lane in range(32):
+                if (starts >> lane) & 1:
+                    A.append(q | (srcs[32 * c + lane] << 16))
+                if (w >> lane) & 1:
+                    q += lens[32 * c + lane]
+        A.append(q)
+        if q >= 65536:
+            continue
+        assert model_table_a_four_slots(lens, srcs, words, o) == A, trial

@@ -592,20 +592,24 @@ def test_fuzz_kernel_configurations():
 
 
 def test_emit_occupancy_follows_the_kept_fraction_and_never_changes_the_bytes():
-    """GM2_CFG_EMIT_OCCUPANCY: auto picks the 4-CTA launch form when the plan kept little of the genome
-    and the 3-CTA form otherwise (default 48 KB tile); forcing either gives the same image."""
+    """GM2_CFG_EMIT_OCCUPANCY: auto picks the 72-register / 3-CTA build, and the 4-CTA one only for small tiles
+    when the plan kept little of the genome; forcing either gives the same image.  GM2_CFG_TILE_BYTES = 0 (the
+    default) sizes the tile from the gene density."""
     g = synth.make_genome(300_000, 280, seed=61)
     starts, ends = g.starts_ends()
     rng = np.random.default_rng(61)
     S = 24
-    for p_keep, want in ((0.05, 4), (0.95, 3)):
+    for tile, p_keep, want in ((0, 0.05, 3), (24576, 0.05, 4), (24576, 0.95, 3)):
         rows = synth.pack_keep_rows(rng.random((S, len(starts))) < p_keep)
         exp_len, _, exp_img = _oracle_image(g.seq, starts, ends, rows, first_idx=0)
         images = {}
         for occ in (0, 3, 4):
             with _native.Context(0) as ctx:
                 ctx.configure(_native.CFG_EMIT_OCCUPANCY, occ)
+                ctx.configure(_native.CFG_TILE_BYTES, tile)
                 ctx.set_reference(g.seq, starts, ends)
+                # 280 genes on 300 kbp: 34 genes' worth of bases is 36 KB
+                assert ctx.query(_native.Q_TILE_BYTES) == (tile or 36864)
                 ctx.load_keep_host(rows)
                 ctx.plan(0)
                 assert np.array_equal(ctx.lengths(), exp_len)

@@ -92,10 +92,11 @@ def main():
                                     got = ctx.diag_range_hashes(image.data_ptr(), nbytes, rec_off[s:s + 2])
                                     ok = ok and int(L[0]) == int(lengths[s]) and int(H[0]) == int(got[0])
                                 ctas = ctx.query(_native.Q_LAST_EMIT_CTAS)
+                                tile_used = ctx.query(_native.Q_TILE_BYTES)
                                 del image
                             alg = nbytes + S * ((F + 7) // 8) + g.G + 16 * F
                             gbs = alg / (ms * 1e-3) / 1e9
-                            ln = (f"{gname:>5} ret {ret:.2f} tile {tile or 49152:6d} frb {frb:7d} mode {mode} occ {occ} ctas {ctas}: "
+                            ln = (f"{gname:>5} ret {ret:.2f} tile {tile_used:6d} frb {frb:7d} mode {mode} occ {occ} ctas {ctas}: "
                                   f"image {nbytes/1e9:6.2f} GB  k_emit {ms:7.3f} ms  {gbs:7.1f} GB/s  frac {gbs/peak:.3f}  "
                                   f"{'ok' if ok else 'MISMATCH'}")
                             print(ln, flush=True)
