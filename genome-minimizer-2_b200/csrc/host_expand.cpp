@@ -61,35 +61,75 @@ static void expand_avx2_aligned(uint8_t* dst, const uint8_t* p, int64_t b0, int6
         r = _mm256_blendv_epi8(r, _mm256_shuffle_epi8(lut1, hi), k3);
         _mm256_stream_si256(reinterpret_cast<__m256i*>(dst), r);
     }
-    _mm_sfence();                                          // this thread's non-temporal stores ordered before it signals completion
 }
 
 // AVX-512 VBMI: 64 bases (128 bits of the stream) -> one whole 64-byte cache line per step, one
 // non-temporal store each (a full line leaves the core in one piece; two 32-byte halves may not).
 // vpermb puts stream bytes 2k, 2k+1, 2k+2 at the bottom of qword k, vpmultishiftqb takes from each
 // qword the 8 fields starting at bit (phase + 2 i) — the bit phase of the stream costs nothing —
-// and vpshufb maps the two low bits of every byte to its letter.  Reads 32 bytes per step from the
-// group's first stream byte (16 used): the caller leaves the last group to the scalar tail.
+// and vpshufb maps the two low bits of every byte to its letter.  The partial line in front of the
+// first aligned one and the one behind the last are the same decode with a byte-masked load (only the
+// stream bytes that exist are touched) and a byte-masked store: a piece costs no scalar work at all.
+// No fence here: the caller fences once per task (expand_task), not once per piece — draining the
+// write-combining buffers ~130 times per record cost a fifth of the decoder's time.
+struct Avx512Tables { alignas(64) uint8_t idx[64], ctl[4][64], lut[64]; };
+static const Avx512Tables& avx512_tables() {
+    static const Avx512Tables t = [] {
+        Avx512Tables x;
+        for (int k = 0; k < 8; ++k)
+            for (int i = 0; i < 8; ++i) {
+                x.idx[8 * k + i] = (uint8_t)(2 * k + (i < 3 ? i : 0));
+                for (int ph = 0; ph < 4; ++ph) x.ctl[ph][8 * k + i] = (uint8_t)(2 * ph + 2 * i);
+            }
+        for (int i = 0; i < 64; ++i) x.lut[i] = (uint8_t)ACGT[i & 3];
+        return x;
+    }();
+    return t;
+}
+
+// n bases starting at base b of the stream p (n <= 64) -> d, byte-masked on both sides: touches only the
+// stream bytes that hold those bases and only the n destination bytes
 __attribute__((target("avx512f,avx512bw,avx512vbmi")))
-static void expand_avx512_aligned(uint8_t* dst, const uint8_t* p, int64_t b0, int64_t ngroups) {
-    alignas(64) uint8_t idx_b[64], ctl_b[64], lut_b[64];
-    const int sh = 2 * (int)(b0 & 3);
-    for (int k = 0; k < 8; ++k)
-        for (int i = 0; i < 8; ++i) {
-            idx_b[8 * k + i] = (uint8_t)(2 * k + (i < 3 ? i : 0));
-            ctl_b[8 * k + i] = (uint8_t)(sh + 2 * i);
-        }
-    for (int i = 0; i < 64; ++i) lut_b[i] = (uint8_t)ACGT[i & 3];
-    const __m512i idx = _mm512_load_si512(idx_b), ctl = _mm512_load_si512(ctl_b), lut = _mm512_load_si512(lut_b);
-    const __m512i m3 = _mm512_set1_epi8(3);
-    const uint8_t* q = p + (b0 >> 2);
-    for (int64_t g = 0; g < ngroups; ++g, q += 16, dst += 64) {
+static inline void avx512_partial(const Avx512Tables& T, uint8_t* d, const uint8_t* p, int64_t b, int n) {
+    const int nb = (int)(((b & 3) + n + 3) >> 2);                          // stream bytes holding those bases (<= 17)
+    const __m512i src = _mm512_maskz_loadu_epi8(((__mmask64)1 << nb) - 1, p + (b >> 2));
+    const __m512i rep = _mm512_permutexvar_epi8(_mm512_load_si512(T.idx), src);
+    const __m512i code = _mm512_and_si512(_mm512_multishift_epi64_epi8(_mm512_load_si512(T.ctl[b & 3]), rep), _mm512_set1_epi8(3));
+    _mm512_mask_storeu_epi8(d, n >= 64 ? ~(__mmask64)0 : (((__mmask64)1 << n) - 1),
+                            _mm512_shuffle_epi8(_mm512_load_si512(T.lut), code));
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vbmi")))
+static void expand_avx512(uint8_t* dst, const uint8_t* p, int64_t nbases) {
+    const Avx512Tables& T = avx512_tables();
+    const __m512i idx = _mm512_load_si512(T.idx), lut = _mm512_load_si512(T.lut), m3 = _mm512_set1_epi8(3);
+    int64_t head = (int64_t)((64 - ((uintptr_t)dst & 63)) & 63);
+    if (head > nbases) head = nbases;
+    if (head) avx512_partial(T, dst, p, 0, (int)head);
+    const int64_t groups = (nbases - head) / 64;
+    const __m512i ctl = _mm512_load_si512(T.ctl[head & 3]);
+    const uint8_t* q = p + (head >> 2);
+    uint8_t* d = dst + head;
+    // every full group reads 32 stream bytes from its first one (17 used); the last group reads exactly what exists
+    for (int64_t g = 0; g + 1 < groups; ++g, q += 16, d += 64) {
+        // the stream was written by the GPU's DMA: it comes from DRAM, and a piece (a few KB) is too short for the
+        // hardware prefetcher to get ahead, so ask for it ~1 KB (64 steps) ahead; past the piece it is the next one's
+        _mm_prefetch(reinterpret_cast<const char*>(q) + 1024, _MM_HINT_T0);
         const __m512i src = _mm512_castsi256_si512(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(q)));
         const __m512i rep = _mm512_permutexvar_epi8(idx, src);
         const __m512i code = _mm512_and_si512(_mm512_multishift_epi64_epi8(ctl, rep), m3);
-        _mm512_stream_si512(reinterpret_cast<__m512i*>(dst), _mm512_shuffle_epi8(lut, code));
+        _mm512_stream_si512(reinterpret_cast<__m512i*>(d), _mm512_shuffle_epi8(lut, code));
     }
-    _mm_sfence();
+    int64_t done = head + 64 * (groups > 0 ? groups - 1 : 0);
+    if (groups > 0) {                                                       // last whole line: exact load, still one NT store
+        const int nb = (int)(((done & 3) + 64 + 3) >> 2);
+        const __m512i src = _mm512_maskz_loadu_epi8(((__mmask64)1 << nb) - 1, p + (done >> 2));
+        const __m512i rep = _mm512_permutexvar_epi8(idx, src);
+        const __m512i code = _mm512_and_si512(_mm512_multishift_epi64_epi8(ctl, rep), m3);
+        _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + done), _mm512_shuffle_epi8(lut, code));
+        done += 64;
+    }
+    if (done < nbases) avx512_partial(T, dst + done, p, done, (int)(nbases - done));
 }
 
 static bool have_avx2() {
@@ -109,15 +149,7 @@ void expand_bases(uint8_t* dst, const uint32_t* words, int64_t nbases, int simd)
     if (simd == 1) simd = simd_level();
     if (simd == 3 && !have_avx512()) simd = 2;
     if (simd == 2 && !have_avx2()) simd = 0;
-    if (simd == 3 && nbases >= 256) {
-        const int64_t head = (int64_t)((64 - ((uintptr_t)dst & 63)) & 63);
-        expand_scalar(dst, p, 0, head);
-        const int64_t groups = (nbases - head) / 64 - 1;            // the last whole group is the scalar tail's (over-read)
-        expand_avx512_aligned(dst + head, p, head, groups);
-        const int64_t done = head + 64 * groups;
-        expand_scalar(dst + done, p, done, nbases - done);
-        return;
-    }
+    if (simd == 3) { if (nbases > 0) expand_avx512(dst, p, nbases); return; }
     if (simd < 2 || nbases < 96) { expand_scalar(dst, p, 0, nbases); return; }
     int64_t head = (int64_t)((32 - ((uintptr_t)dst & 31)) & 31);
     expand_scalar(dst, p, 0, head);
@@ -158,9 +190,14 @@ static void expand_task(const ChunkView& v, int64_t task) {
     const int t0 = (int)((int64_t)v.ntiles * part / TASKS_PER_SAMPLE), t1 = (int)((int64_t)v.ntiles * (part + 1) / TASKS_PER_SAMPLE);
     for (int t = t0; t < t1; ++t) {
         const int64_t a = toff[t], b = t + 1 < v.ntiles ? toff[t + 1] : len;
+        if (t + 1 < t1) {                                  // the next piece's stream starts somewhere else: ask for it now
+            const char* nx = reinterpret_cast<const char*>(v.packed + wbase + (b >> 4) + t + 1);
+            _mm_prefetch(nx, _MM_HINT_T0); _mm_prefetch(nx + 64, _MM_HINT_T0); _mm_prefetch(nx + 128, _MM_HINT_T0);
+        }
         if (b > a) expand_bases(seq + a, v.packed + wbase + (a >> 4) + t, b - a, v.simd);
     }
     if (part == TASKS_PER_SAMPLE - 1) seq[len] = '\n';
+    _mm_sfence();                                          // this thread's non-temporal stores ordered before it signals completion
 }
 
 // ---- persistent workers: a chunk is decoded every ~100 microseconds, so workers first SPIN on the job
