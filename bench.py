@@ -81,6 +81,8 @@ def parse_args():
     ap.add_argument("--emit-occupancy", type=int, default=-1, help="GM2_CFG_EMIT_OCCUPANCY (0 auto, 3, 4)")
     ap.add_argument("--emit-debug", type=int, default=0, help="timing experiments only (wrong output)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-pipeline", action="store_true", help="one context for every step (the plan of step k+1 does not start before the emit of step k has finished)")
+    ap.add_argument("--stream-priorities", default="-1,0", help="CUDA priorities of the two contexts' streams (lower = higher)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
@@ -559,8 +561,10 @@ def retention_sweep(ctx_k12, g_k12, make_ctx, torch, dev, stream, peak, retentio
 # ----------------------------------------------------------------------------------------------
 # config 3: the fixed 100,000-sample job over the N ranks
 # ----------------------------------------------------------------------------------------------
-def sharded_device_leg(ctx, g, job: Job, torch, dist, dev, stream, rank, world, barrier, chunk_samples):
-    """Every rank streams its count-based shard of the fixed job through a ring of two output buffers."""
+def sharded_device_leg(pair, g, job: Job, torch, dist, dev, stream, rank, world, barrier, chunk_samples):
+    """Every rank streams its count-based shard of the fixed job through a ring of two output buffers, chunk i on
+    context i & 1: chunk i+1 is planned under the emit of chunk i (gm2_order_after keeps the emits in order)."""
+    ctx = pair[0]
     from genome_minimizer_2_b200 import engine
     lo, hi = engine.shard_range(job.total, rank, world)
     chunks = [(a, min(a + chunk_samples, hi)) for a in range(lo, hi, chunk_samples)]
@@ -582,11 +586,15 @@ def sharded_device_leg(ctx, g, job: Job, torch, dist, dev, stream, rank, world, 
     all_len = torch.zeros(width * world, dtype=torch.int64, device=dev)
 
     def run():
+        pair[1].order_after(pair[0])
         for i, ((a, b), (d_ids, d_off, n)) in enumerate(zip(chunks, staged)):
-            ctx.load_ids_dev(d_ids.data_ptr(), d_off.data_ptr(), b - a, n)
-            ctx.plan_async(a)
-            ctx.emit_dev(0, b - a, ring[i & 1].data_ptr(), cap)
-            ctx.lengths_dev(my_len.data_ptr() + 8 * (a - lo))
+            c, o = pair[i & 1], pair[(i + 1) & 1]
+            c.load_ids_dev(d_ids.data_ptr(), d_off.data_ptr(), b - a, n)
+            c.plan_async(a)                                   # under the other context's emit of chunk i-1
+            c.lengths_dev(my_len.data_ptr() + 8 * (a - lo))
+            c.order_after(o)                                  # emits in file order; ring[i & 1] is this context's own
+            c.emit_dev(0, b - a, ring[i & 1].data_ptr(), cap)
+        pair[0].order_after(pair[1])                          # stream A (the timing / collective stream) sees everything
         if world > 1:
             dist.all_gather_into_tensor(all_len, my_len)
         else:
@@ -740,7 +748,7 @@ def main():
     job = Job(table, S * world, args.retention, args.noise_ids, seed=2)
     ids, off, _ = job.csr(first_idx, first_idx + S)
 
-    def make_ctx():
+    def make_ctx(on_stream=None):
         c = _native.Context(local_rank)
         for key, val, on in ((_native.CFG_TILE_BYTES, args.tile_bytes, args.tile_bytes > 0),
                              (_native.CFG_PACKING, args.packing, args.packing > 0),
@@ -757,25 +765,36 @@ def main():
                              (_native.CFG_DEBUG, args.emit_debug, args.emit_debug != 0)):
             if on:
                 c.configure(key, val)
-        c.set_stream(stream.cuda_stream)
+        c.set_stream((on_stream or stream).cuda_stream)
         return c
 
     if args.emit_debug:
         args.verify = 0
-    # a real (non-default) torch stream: the kernels are launched on it and the CUDA events below are
-    # recorded on it.  (torch's default stream has handle 0, which gm2_set_stream reads as "own stream".)
-    stream = torch.cuda.Stream(dev)
+    # real (non-default) torch streams: the kernels are launched on them and the CUDA events below are
+    # recorded on them.  (torch's default stream has handle 0, which gm2_set_stream reads as "own stream".)
+    prio = [int(x) for x in args.stream_priorities.split(",")]
+    stream = torch.cuda.Stream(dev, priority=prio[0])
+    stream_b = torch.cuda.Stream(dev, priority=prio[1])
     torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
+    assert stream.cuda_stream != 0 and stream_b.cuda_stream != 0
+    # Two contexts on two streams take the steps in turn: a context is one plan slot, so step k runs on context
+    # k & 1 and its plan (K1-K3, issue/latency-bound) is issued while the other context's emit of step k-1
+    # (write-bound) is still running; gm2_order_after keeps the emits themselves one after the other:
+    #   stream A:  plan(k) | .......... emit(k) .......... |                  plan(k+2) | ....
+    #   stream B:            plan(k+1) |                     .......... emit(k+1) ..........
     ctx = make_ctx()
-    ctx.set_reference(g.seq, starts, ends)
-    ctx.set_name_map(table.id2gene_off, table.id2gene_idx)
+    ctx_b = ctx if args.no_pipeline else make_ctx(stream_b)
+    pair = (ctx, ctx_b)
+    streams = (stream, stream if args.no_pipeline else stream_b)
 
     # device-resident inputs
     d_ids = torch.from_numpy(ids).to(dev)
     d_off = torch.from_numpy(off).to(dev)
-    ctx.load_ids_dev(d_ids.data_ptr(), d_off.data_ptr(), S, ids.size)
-    ctx.plan(first_idx)                        # sizing pass (outside the timed region)
+    for c in set(pair):
+        c.set_reference(g.seq, starts, ends)
+        c.set_name_map(table.id2gene_off, table.id2gene_idx)
+        c.load_ids_dev(d_ids.data_ptr(), d_off.data_ptr(), S, ids.size)
+        c.plan(first_idx)                      # sizing pass (outside the timed region)
     lengths = ctx.lengths()
     rec_off = ctx.record_offsets()
     image_bytes = int(rec_off[-1])
@@ -784,11 +803,20 @@ def main():
     my_len = torch.zeros(S, dtype=torch.int64, device=dev)
     all_len = torch.zeros(S * world, dtype=torch.int64, device=dev)
 
-    def step():
-        ctx.plan_async(first_idx)
-        ctx.emit_dev(0, S, image.data_ptr(), image_bytes)
+    def step(k, ev=None):
+        """One pass over the batch on context k & 1.  ev: optional [plan issued, emit start, emit end] events."""
+        c, o, st = pair[k & 1], pair[(k + 1) & 1], streams[k & 1]
+        if ev: ev[0].record(st)
+        c.plan_async(first_idx)                # runs under the other context's emit of step k-1
+        if world > 1:
+            c.lengths_dev(my_len.data_ptr())
+            if c is not ctx:
+                ctx.order_after(c)             # the collective is issued on stream A: this step's lengths first
+        c.order_after(o)                       # emit(k) after emit(k-1)
+        if ev: ev[1].record(st)
+        c.emit_dev(0, S, image.data_ptr(), image_bytes)
+        if ev: ev[2].record(st)
         if world > 1:                          # this step's per-sample lengths -> every rank (global file offsets)
-            ctx.lengths_dev(my_len.data_ptr())
             dist.all_gather_into_tensor(all_len, my_len)
 
     def barrier():
@@ -796,36 +824,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for k in range(2 * ((max(args.warmup, 3) + 1) // 2)):
+        step(k)
     barrier()
 
-    # timed region: exactly K steps, CUDA events on the launching stream, clocks sampled meanwhile
+    # the plan and k_emit alone (nothing else on the GPU): the plan's own cost, and k_emit unperturbed
+    solo = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    solo_plan, solo_emit = [], []
+    for _ in range(3):
+        solo[0].record(stream)
+        ctx.plan_async(first_idx)
+        solo[1].record(stream)
+        ctx.emit_dev(0, S, image.data_ptr(), image_bytes)
+        solo[2].record(stream)
+        torch.cuda.synchronize(dev)
+        solo_plan.append(solo[0].elapsed_time(solo[1]))
+        solo_emit.append(solo[1].elapsed_time(solo[2]))
+    barrier()
+
+    # timed region: exactly K steps, CUDA events on the launching streams, clocks sampled meanwhile
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    l0 = ctx.query(_native.Q_LAUNCHES)
+    l0 = sum(c.query(_native.Q_LAUNCHES) for c in set(pair))
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_stop = torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
+    ctx_b.order_after(ctx)                     # stream B starts inside the timed region
     for k in range(args.steps):
-        ev[k][0].record(stream)
-        ctx.plan_async(first_idx)
-        ev[k][1].record(stream)
-        ctx.emit_dev(0, S, image.data_ptr(), image_bytes)
-        ev[k][2].record(stream)
-        if world > 1:
-            ctx.lengths_dev(my_len.data_ptr())
-            dist.all_gather_into_tensor(all_len, my_len)
+        step(k, ev[k])
+    ctx.order_after(ctx_b)                     # ... and ends inside it
     t_stop.record(stream)
     barrier()
-    launches = ctx.query(_native.Q_LAUNCHES) - l0
+    launches = sum(c.query(_native.Q_LAUNCHES) for c in set(pair)) - l0
     total_ms = t_start.elapsed_time(t_stop)
-    plan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    emit_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    emit_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))   # k_emit inside the timed region (a plan may run beside it)
+    plan_ms = float(np.mean(solo_plan))        # the plan alone; inside the timed region it runs under the previous step's emit
     clocks = sampler.stop() if rank == 0 else None
     emit_ctas = ctx.query(_native.Q_LAST_EMIT_CTAS)
     tile_bytes_used = ctx.query(_native.Q_TILE_BYTES)
@@ -892,7 +929,7 @@ def main():
     if not args.no_sharded and args.genome == "k12" and not args.emit_debug:
         job3 = Job(table, args.job_samples, args.retention, args.noise_ids, seed=3)
         sharded = {"job": f"C3: {args.job_samples} samples, K-12-shaped genome, gene retention {args.retention}, cut over {world} rank(s)",
-                   "device": sharded_device_leg(ctx, g, job3, torch, dist, dev, stream, rank, world, barrier, S)}
+                   "device": sharded_device_leg(pair, g, job3, torch, dist, dev, stream, rank, world, barrier, S)}
         sharded["file"] = sharded_file_leg(g, table, job3, rank, world, barrier, args.file_gb_per_rank)
     dropin = None
     if not args.no_dropin and args.genome == "k12":
@@ -1022,7 +1059,12 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_emit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms, "plan_ms": plan_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": emit_ms,
+                "kernel_ms_alone": float(np.mean(solo_emit)), "frac_alone": alg_bytes / (float(np.mean(solo_emit)) * 1e-3) / 1e9 / peak,
+                "plan_ms": plan_ms,
+                "plan_overlap": ("none (--no-pipeline)" if args.no_pipeline else
+                                 "the plan (K1-K3) of step k+1 runs under k_emit of step k: two contexts on two streams take the "
+                                 "steps in turn, gm2_order_after keeps the emits in order; plan_ms is the plan alone"),
                 "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None,
                 "write_fill_gbs": fill_gbs}
 

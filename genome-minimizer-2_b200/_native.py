@@ -36,6 +36,7 @@ SIGNATURES = {
     "gm2_query": (_c.c_int, [_P, _c.c_int, _c.POINTER(_I64)]),
     "gm2_set_stream": (_c.c_int, [_P, _P]),
     "gm2_sync": (_c.c_int, [_P]),
+    "gm2_order_after": (_c.c_int, [_P, _P]),
     "gm2_set_reference": (_c.c_int, [_P, _P, _I64, _P, _P, _c.c_int32]),
     "gm2_set_name_map": (_c.c_int, [_P, _P, _P, _c.c_int32]),
     "gm2_set_header_prefix": (_c.c_int, [_P, _c.c_char_p]),
@@ -281,6 +282,10 @@ class Context:
 
     def set_stream(self, cuda_stream: Optional[int]):
         self._ck(self._lib.gm2_set_stream(self._h, cuda_stream))
+
+    def order_after(self, other: "Context"):
+        """Work issued on this context from now on starts after everything issued on `other` so far."""
+        self._ck(self._lib.gm2_order_after(self._h, other._h))
 
     def sync(self):
         self._ck(self._lib.gm2_sync(self._h))

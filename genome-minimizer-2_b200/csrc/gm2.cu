@@ -58,6 +58,7 @@ struct gm2_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_emit[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_order = nullptr;       // gm2_order_after
     std::string err;
     uint64_t launches = 0;
 
@@ -261,6 +262,7 @@ GM2_API int gm2_destroy(gm2_ctx* c) {
     if (c->h_rec_off) cudaFreeHost(c->h_rec_off);
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->ev_total) cudaEventDestroy(c->ev_total);
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
     delete c->pool;
     for (int i = 0; i < 3; ++i) {
         if (c->d_pstage[i]) cudaFree(c->d_pstage[i]);
@@ -356,6 +358,18 @@ GM2_API int gm2_sync(gm2_ctx* c) {
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->copy_stream));
+    return GM2_OK;
+}
+
+GM2_API int gm2_order_after(gm2_ctx* c, gm2_ctx* other) {
+    if (!c || !other) return GM2_ERR_INVALID;
+    if (c == other) return GM2_OK;                                   // a stream is already ordered with itself
+    if (c->device != other->device) return fail(c, GM2_ERR_INVALID, "gm2_order_after: the contexts are on different devices");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->ev_order) CU(c, cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+    // the event is re-recorded per call: a wait captures the record that precedes it, later records do not move it
+    CU(c, cudaEventRecord(c->ev_order, other->stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_order, 0));
     return GM2_OK;
 }
 

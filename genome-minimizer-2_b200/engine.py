@@ -377,6 +377,56 @@ class MinimizerEngine:
         return total
 
 
+class ContextPair:
+    """Two contexts over one reference on one GPU, for device-resident pipelines.
+
+    A context is ONE plan slot (its plan state is overwritten by its next plan), so a job that is processed
+    chunk by chunk with the output staying on the GPU alternates two of them: chunk i goes to context i & 1,
+    `gm2_order_after` keeps the emits in file order on the device, and the plan of chunk i+1 (K1-K3:
+    issue/latency-bound) runs on the other context's stream UNDER the emit of chunk i (write-bound) instead of
+    between two emits.  Nothing blocks on the host.  (The host paths — gm2_emit_host, drain — leave the GPU
+    idle most of the time anyway and use one context.)"""
+
+    def __init__(self, seq: np.ndarray, table: GeneTable, device: Optional[int] = None,
+                 config: Optional[Dict[int, int]] = None, streams: Optional[Sequence[int]] = None):
+        dev = default_device() if device is None else int(device)
+        self.table = table
+        self.ctx = [_native.Context(dev), _native.Context(dev)]
+        for i, c in enumerate(self.ctx):
+            for k, v in (config or {}).items():
+                c.configure(k, v)
+            if streams is not None:
+                c.set_stream(streams[i])
+            c.set_reference(np.ascontiguousarray(seq, dtype=np.uint8), table.starts, table.ends)
+            c.set_name_map(table.id2gene_off, table.id2gene_idx)
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+    def run_chunks(self, chunks: Iterable[Tuple[int, int, int, int, int]], ring: Sequence[Tuple[int, int]],
+                   after_emit: Optional[Callable[[int, "_native.Context"], None]] = None) -> int:
+        """chunks: (ids_dev_ptr, off_dev_ptr, samples, n_ids, first_idx) of device-resident CSR id lists, in file
+        order; ring: two (dev_ptr, capacity) output buffers, chunk i is emitted into ring[i & 1].
+        `after_emit(i, ctx)` may issue the chunk's consumer on ctx's stream (hashing, a copy, ...): ring[i & 1] is
+        not overwritten before that work has finished.  Returns the number of chunks issued; call sync() on both
+        contexts (or order a stream after them) before reading results on the host."""
+        a, b = self.ctx
+        b.order_after(a)
+        n = 0
+        for i, (ids_ptr, off_ptr, S, n_ids, first_idx) in enumerate(chunks):
+            c, o = self.ctx[i & 1], self.ctx[(i + 1) & 1]
+            c.load_ids_dev(ids_ptr, off_ptr, S, n_ids)
+            c.plan_async(first_idx)
+            c.order_after(o)
+            c.emit_dev(0, S, ring[i & 1][0], ring[i & 1][1])
+            if after_emit is not None:
+                after_emit(i, c)
+            n += 1
+        a.order_after(b)
+        return n
+
+
 def drain_to_file(eng, target, file_pos: int, s0: int = 0, s1: Optional[int] = None,
                   progress: Optional[Callable[[int, int], None]] = None) -> int:
     """Records [s0,s1) into `target` (a path, or an open read-write descriptor that stays open) starting at

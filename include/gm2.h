@@ -103,6 +103,13 @@ int         gm2_query(const gm2_ctx* ctx, int key, int64_t* out);
  * default stream pass cudaStreamLegacy ((void*)0x1) explicitly. */
 int         gm2_set_stream(gm2_ctx* ctx, void* cuda_stream);
 int         gm2_sync(gm2_ctx* ctx);
+/* Pipelines over several contexts of one GPU (a context is one plan slot: its plan state is overwritten
+ * by its next gm2_plan).  Device work issued on `ctx` AFTER this call starts only when everything issued
+ * on `other` BEFORE this call has finished; nothing blocks on the host.  Two contexts on the same
+ * reference, chunk i on context i & 1:   load(i); plan_async(i); order_after(ctx[i&1], ctx[~i&1]);
+ * emit_dev(i)   keeps the emits in file order on the device while chunk i+1 is planned under emit i
+ * (bench.py, engine.ContextPair). */
+int         gm2_order_after(gm2_ctx* ctx, gm2_ctx* other);
 
 /* The record:  replaces `record.seq` (minimizer_2.py:35, :94) and, for every feature
  * with type == "gene" in file order, `int(feature.location.start)` /

@@ -144,3 +144,57 @@ def test_config5_width_55039_keep_rows_counts_and_records():
         assert np.array_equal(l4, exp_len[5:9])
     finally:
         eng.close()
+
+
+def test_context_pair_pipeline_is_byte_identical_and_ordered():
+    """engine.ContextPair / gm2_order_after: six chunks of device-resident id lists alternate between two contexts
+    on two streams (plan of chunk i+1 under the emit of chunk i); each chunk's image is hashed on the device right
+    after its emit and must match the oracle, although the ring holds only two chunks."""
+    import torch
+    g = synth.make_genome(400_000, 380, seed=71, nested=6, overlap_frac=0.3)
+    starts, ends = g.starts_ends()
+    table = engine.GeneTable(g.gene_names(), starts, ends)
+    rng = np.random.default_rng(71)
+    name_ids = np.asarray([table.name_to_id[n] for n in table.names], dtype=np.int64)
+    nchunks, Sc = 6, 40
+    chunks, expect, keep_dev = [], [], []
+    for i in range(nchunks):
+        keep = rng.random((Sc, table.V)) < (0.15 + 0.14 * i)
+        ids = [np.flatnonzero(row).astype(np.int32) for row in keep]
+        off = np.zeros(Sc + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(x) for x in ids])
+        flat = np.concatenate(ids) if off[-1] else np.zeros(1, dtype=np.int32)
+        d_ids, d_off = torch.from_numpy(flat).to("cuda:0"), torch.from_numpy(off).to("cuda:0")
+        keep_dev.append((d_ids, d_off))
+        chunks.append((d_ids.data_ptr(), d_off.data_ptr(), Sc, int(off[-1]), i * Sc))
+        gene_keep = keep[:, name_ids]                                        # genes sharing a name are kept together
+        expect.append(c_oracle.batch(g.seq, starts, ends, synth.pack_keep_rows(gene_keep), first_idx=i * Sc))
+    cap = max(int((e[0] + 64).sum()) for e in expect)
+    ring = [torch.empty(cap, dtype=torch.uint8, device="cuda:0") for _ in range(2)]
+    pair = engine.ContextPair(g.seq, table, device=0)
+    try:
+        got = [None] * nchunks
+        offs = [np.concatenate([[0], np.cumsum(1 + len(engine.SEQ_ID_PREFIX) + np.char.str_len((np.arange(i * Sc, (i + 1) * Sc) + 1).astype(str)) + 1 + expect[i][0] + 1)]).astype(np.int64)
+                for i in range(nchunks)]
+
+        def after_emit(i, ctx):
+            # enqueued on the chunk's own stream, right behind its emit; returns host data => that stream is synchronised,
+            # while the OTHER context's plan / emit of the next chunk keeps running
+            got[i] = ctx.diag_range_hashes(ring[i & 1].data_ptr(), cap, offs[i])
+
+        assert pair.run_chunks(chunks, [(r.data_ptr(), cap) for r in ring], after_emit) == nchunks
+        for c in pair.ctx:
+            c.sync()
+        for i in range(nchunks):
+            assert np.array_equal(got[i], expect[i][1]), i
+        # the same schedule without host round trips in between: only the last two chunks remain in the ring
+        pair.run_chunks(chunks, [(r.data_ptr(), cap) for r in ring])
+        for c in pair.ctx:
+            c.sync()
+        for i in (nchunks - 2, nchunks - 1):
+            assert np.array_equal(pair.ctx[i & 1].diag_range_hashes(ring[i & 1].data_ptr(), cap, offs[i]), expect[i][1]), i
+            assert np.array_equal(pair.ctx[i & 1].lengths(), expect[i][0])
+    finally:
+        pair.close()
+    with _native.Context(0) as a:
+        assert a.order_after(a) is None                                      # ordering a context after itself is a no-op
