@@ -11,7 +11,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 SRC = os.path.join(PKG_DIR, "csrc", "gm2.cu")
 HOST_SRC = [os.path.join(PKG_DIR, "csrc", "host_expand.cpp")]      # host-only C++, compiled by nvcc's host compiler
 HDR = os.path.join(REPO_ROOT, "include", "gm2.h")
-LIB = os.path.join(PKG_DIR, "libgm2.so")
+LIB = os.environ.get("GM2_LIB") or os.path.join(PKG_DIR, "libgm2.so")     # GM2_LIB: another build of the library (A/B runs)
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -44,6 +44,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_ROOT, "include"), "-o", LIB, SRC, *HOST_SRC]
     if os.environ.get("GM2_EMIT_DEBUG"):          # timing knock-outs in k_emit (wrong output): experiments only
         cmd.insert(1, "-DGM2_EMIT_DEBUG")
+    for flag in os.environ.get("GM2_NVCC_EXTRA", "").split():      # e.g. -DGM2_EXP_...=1 for an experiment build
+        cmd.insert(1, flag)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

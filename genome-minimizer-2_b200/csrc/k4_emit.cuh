@@ -443,6 +443,25 @@ __device__ __forceinline__ uint4 lds_unaligned16(uint32_t a) {
     o.w = __funnelshift_r(w3, w4, sh);
     return o;
 }
+// lds_unaligned16 when only bytes [b0, b1) of the window will be used (0 <= b0 < b1 <= 16): an aligned half that
+// holds none of them is not loaded.  Lanes of the boundary-vector pass read unrelated addresses, so every lane
+// that drops out of a load saves a wavefront on the L1 data pipe (the limiter at low retention).
+__device__ __forceinline__ uint4 lds_unaligned16_part(uint32_t a, int b0, int b1) {
+    const uint32_t qa = a & ~15u;
+    const int m = (int)(a & 15u), sh = (int)(a & 3u) * 8;
+    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+    if (m + b0 < 16) lo = lds128(qa);
+    if (m + b1 > 16) hi = lds128(qa + 16);
+    uint32_t w0 = lo.x, w1 = lo.y, w2 = lo.z, w3 = lo.w, w4 = hi.x, w5 = hi.y, w6 = hi.z;
+    if (a & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = hi.w; }
+    if (a & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, sh);
+    o.y = __funnelshift_r(w1, w2, sh);
+    o.z = __funnelshift_r(w2, w3, sh);
+    o.w = __funnelshift_r(w3, w4, sh);
+    return o;
+}
 // bytes [0, k) of x, bytes [k, 16) of y  (0 <= k <= 16).  Word w takes its low clamp(8k - 32w, 0, 32) bits from x:
 // the clamped funnel shift turns that bit count into the mask without a table.
 __device__ __forceinline__ uint4 merge16(const uint4& x, const uint4& y, int k) {
@@ -557,12 +576,14 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
                 uint4 ov;
                 if (!slow) {
                     const uint32_t sa = has_prev ? xm : x, sb = has_prev ? x : x1, sc = has_prev ? x1 : x2;
-                    const uint4 X = lds_unaligned16(tile_a + (sa >> 16) + (uint32_t)(p0 - (int)(sa & 0xffffu)));
-                    const uint4 Y = lds_unaligned16(tile_a + (sb >> 16) + (uint32_t)(p0 - (int)(sb & 0xffffu)));
-                    ov = merge16(X, Y, (int)(sb & 0xffffu) - p0);
+                    const int kb = (int)(sb & 0xffffu) - p0;                      // bytes [0, kb) from source a, [kb, kc) from b
+                    const int kc = nsrc == 3 ? (int)(sc & 0xffffu) - p0 : 16;     // ... and [kc, 16) from c
+                    const uint4 X = lds_unaligned16_part(tile_a + (sa >> 16) + (uint32_t)(p0 - (int)(sa & 0xffffu)), 0, kb);
+                    const uint4 Y = lds_unaligned16_part(tile_a + (sb >> 16) + (uint32_t)(p0 - (int)(sb & 0xffffu)), kb, kc);
+                    ov = merge16(X, Y, kb);
                     if (nsrc == 3) {
-                        const uint4 Z = lds_unaligned16(tile_a + (sc >> 16) + (uint32_t)(p0 - (int)(sc & 0xffffu)));
-                        ov = merge16(ov, Z, (int)(sc & 0xffffu) - p0);
+                        const uint4 Z = lds_unaligned16_part(tile_a + (sc >> 16) + (uint32_t)(p0 - (int)(sc & 0xffffu)), kc, 16);
+                        ov = merge16(ov, Z, kc);
                     }
                 } else {                                                          // many tiny runs in one vector
                     int rc = has_prev ? r - 1 : r;
