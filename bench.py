@@ -1022,6 +1022,11 @@ def main():
                "delivered_image_gbs_per_gpu": delivered,
                "host_write_ceiling_gbs_per_rank": fill_host,
                "e2e_frac_of_host_ceiling": delivered / fill_host if fill_host else None,
+               # what the transport moves through the host's memory controllers per delivered byte: the image itself,
+               # plus (two-bit form) 0.25 B written by the DMA and 0.25 B read back by the decoder, or (image bytes)
+               # 1 B written by the DMA and read back by the copy into the caller's buffer
+               "host_memory_traffic_gbs_per_rank": delivered * (1.5 if wire_used == 2 else 3.0),
+               "host_traffic_frac_of_host_ceiling": (delivered * (1.5 if wire_used == 2 else 3.0) / fill_host) if fill_host else None,
                "raw_pinned_d2h_gbs_per_gpu": raw_gbs,
                "transport": ("two bits per base over PCIe (k_emit_packed), expanded into the caller's buffer by host threads"
                              if wire_used == 2 else "image bytes over PCIe (k_emit)"),
