@@ -570,7 +570,7 @@ def test_fuzz_kernel_configurations():
         first = int(rng.choice([0, 9, 99, 12345, 99_999_990]))
         exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows, first_idx=first)
         cfg = {
-            _native.CFG_TILE_BYTES: int(rng.choice([4096, 8192, 16384, 32768, 49152, 65536, 131072])),
+            _native.CFG_TILE_BYTES: int(rng.choice([0, 4096, 8192, 16384, 32768, 49152, 65536, 131072])),
             _native.CFG_EMIT_WARPS: int(rng.choice([1, 2, 4, 8])),
             _native.CFG_RUN_TABLE: int(rng.choice([32, 34, 64, 128])),
             _native.CFG_PACKING: int(rng.choice([1, 2])),
