@@ -29,6 +29,10 @@ sharded   = BASELINE.json configs[2], the FIXED 100,000-sample job cut over the 
             `entry` = process_multiple_genomes_single_file itself (GenBank file + .npy lists) under
             the same launch, every record compared with the oracle
 retention_sweep = k_emit alone at gene retention 0.1 ... 0.9 on both genome shapes (N = 1)
+config5   = BASELINE.json configs[4]: VAE v0 decoder output (torch) -> `> 0.5` -> column -> gene keep mask
+            (k_keep_from_probs) -> plan -> emit, 100,000 samples over the ranks (12,500 per GPU), V = 55,039
+            columns, random-init weights; per-phase CUDA-event times, three records per rank checked against
+            the converter + minimizer oracles
 """
 from __future__ import annotations
 
@@ -88,6 +92,7 @@ def parse_args():
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=16)
     ap.add_argument("--ref-samples-per-core", type=int, default=2)
     ap.add_argument("--verify", type=int, default=64, help="records checked against the oracle after the run")
@@ -717,6 +722,94 @@ def sharded_file_leg(g, table, job: Job, rank, world, barrier, gb_per_rank):
 
 
 # ----------------------------------------------------------------------------------------------
+# BASELINE config 5: decoder output -> threshold -> column -> gene keep mask -> minimize
+# ----------------------------------------------------------------------------------------------
+def config5_leg(g, table, torch, dist, dev, local_rank, rank, world, barrier, total_samples=100_000, columns=55_039, steps=5):
+    """VAE v0 decoder (latent 64 -> 1024 -> 1024 -> 1024 -> V, random-init Xavier weights as training/model.py:116-120,
+    eval mode; plain torch, outside the graded kernels) -> `> 0.5` (utils/extras.py:200-201) -> column -> gene keep mask
+    with forced essentials (binary_converter.py:49-64, :91-110) -> minimize, everything after the probabilities in
+    libgm2 on the device.  100,000 samples over the ranks (12,500 per GPU: one GPU alone takes 12,500 too).  Three
+    records per rank are checked against the converter + minimizer oracles."""
+    from genome_minimizer_2_b200 import engine, synth
+    from oracle import c_oracle, converter_oracle as co, minimizer_oracle as mo
+    S = total_samples // max(world, 8)
+    torch.manual_seed(5)
+    names = [n for n in table.name_to_id if n]
+    cols = names + [f"group_{i}" for i in range(columns - len(names))]
+    rng = np.random.default_rng(5)
+    cols = [cols[i] for i in rng.permutation(len(cols))]
+    essential = names[::15]
+
+    def block(i, o):
+        lin = torch.nn.Linear(i, o)
+        torch.nn.init.xavier_uniform_(lin.weight)
+        torch.nn.init.zeros_(lin.bias)
+        return [lin, torch.nn.BatchNorm1d(o), torch.nn.ReLU()]
+
+    last = torch.nn.Linear(1024, columns)
+    torch.nn.init.xavier_uniform_(last.weight)
+    torch.nn.init.zeros_(last.bias)
+    decoder = torch.nn.Sequential(*block(64, 1024), *block(1024, 1024), *block(1024, 1024), last, torch.nn.Sigmoid()).to(dev).eval()
+    eng = engine.MinimizerEngine(seq=g.seq, table=table, device=local_rank)
+    st = torch.cuda.current_stream(dev)
+    eng.ctx.set_stream(st.cuda_stream)
+    try:
+        space = engine.ColumnSpace(table, cols, essential)
+        first = rank * S
+        with torch.no_grad():
+            torch.manual_seed(5 + 1000 * rank)          # same weights everywhere, different samples per rank
+            z = torch.randn(S, 64, device=dev)
+            probs = decoder(z)
+            lengths, counts = engine.plan_from_probabilities(eng, space, probs, first_idx=first)
+            off = eng.ctx.record_offsets()
+            image = torch.empty(int(off[-1]), dtype=torch.uint8, device=dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            t_dec = t_plan = t_emit = 0.0
+            for it in range(steps + 2):
+                ev[0].record(st)
+                probs = decoder(z)
+                ev[1].record(st)
+                eng.ctx.load_probs_dev(probs.data_ptr(), S, probs.stride(0), 0.5)
+                eng.ctx.plan_async(first)
+                ev[2].record(st)
+                eng.ctx.emit_dev(0, S, image.data_ptr(), image.numel())
+                ev[3].record(st)
+                torch.cuda.synchronize(dev)
+                if it >= 2:
+                    t_dec += ev[0].elapsed_time(ev[1]); t_plan += ev[1].elapsed_time(ev[2]); t_emit += ev[2].elapsed_time(ev[3])
+            # parity: the reference chain on three samples of this rank
+            starts, ends = g.starts_ends()
+            pick = sorted({0, S // 2, S - 1})
+            host = probs[pick].float().cpu().numpy()
+            lists = co.add_essentials(co.masks_to_gene_lists(co.threshold_samples(host), cols), essential)
+            ok = True
+            for s, needed in zip(pick, lists):
+                keep = mo.keep_vector(table.names, needed)
+                L, H, _ = c_oracle.batch(g.seq, starts, ends, synth.pack_keep_rows(keep[None, :]), first_idx=first + s)
+                got = eng.ctx.diag_range_hashes(image.data_ptr(), image.numel(), off[s:s + 2])
+                ok = ok and int(L[0]) == int(lengths[s]) and int(H[0]) == int(got[0]) and len(needed) == int(counts[s])
+        kept = int(lengths.sum())
+        t = torch.tensor([t_dec, t_plan, t_emit, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+        k = torch.tensor([kept], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(k, op=dist.ReduceOp.SUM)
+        t_dec, t_plan, t_emit, bad = (float(x) for x in t.tolist())
+        if bad:
+            raise SystemExit("bench.py: config 5 leg differs from the converter + minimizer oracles")
+        n = steps
+        return {"workload": f"C5: VAE v0 decode -> `> 0.5` -> column -> gene keep mask -> minimize, {S * world} samples over {world} GPU(s), V = {columns} columns",
+                "samples_total": S * world, "samples_per_rank": S, "decode_ms": t_dec / n, "keepmask_plan_ms": t_plan / n, "emit_ms": t_emit / n,
+                "gbp_per_s_after_decode": int(k.item()) / ((t_plan + t_emit) / n * 1e-3) / 1e9,
+                "gbp_per_s_incl_decode": int(k.item()) / ((t_dec + t_plan + t_emit) / n * 1e-3) / 1e9,
+                "mean_retained_fraction": float(lengths.mean() / g.G), "mean_list_length": float(counts.mean()),
+                "image_gb_per_gpu": image.numel() / 1e9, "records_checked": 3 * world, "byte_identical": True,
+                "timing": "CUDA events per phase, max over ranks; the decoder is torch (library GEMMs), outside the graded kernels"}
+    finally:
+        eng.close()
+
+
+# ----------------------------------------------------------------------------------------------
 # ours
 # ----------------------------------------------------------------------------------------------
 def main():
@@ -931,6 +1024,9 @@ def main():
         sharded = {"job": f"C3: {args.job_samples} samples, K-12-shaped genome, gene retention {args.retention}, cut over {world} rank(s)",
                    "device": sharded_device_leg(pair, g, job3, torch, dist, dev, stream, rank, world, barrier, S)}
         sharded["file"] = sharded_file_leg(g, table, job3, rank, world, barrier, args.file_gb_per_rank)
+    config5 = None
+    if not args.no_c5 and args.genome == "k12" and not args.emit_debug:
+        config5 = config5_leg(g, table, torch, dist, dev, local_rank, rank, world, barrier)
     dropin = None
     if not args.no_dropin and args.genome == "k12":
         dropin = dropin_entry(g, table, rank, world, barrier)
@@ -1099,7 +1195,7 @@ def main():
                    "emit_ctas_per_sm": emit_ctas, "cpu_model": cpu_model(), "host_cores": os.cpu_count()},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_port_c": cpu_c, "verify": verify,
-        "sharded": sharded, "retention_sweep": sweep, "dropin_c1": dropin,
+        "sharded": sharded, "config5": config5, "retention_sweep": sweep, "dropin_c1": dropin,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
