@@ -831,6 +831,16 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     const int64_t blocks = nbatch * tiles;
     if (blocks > 0x7fffffffLL) return fail(c, GM2_ERR_INVALID, "gm2_emit: grid too large; emit a smaller sample range");
     EmitParams p;
+    poll_kept_frac(c);
+    // Short-run form: the bitmap-indexed whole-visit form (2) is at least as fast as the per-batch cursor form (1)
+    // at every retention measured (0.1 ... 0.9, both genome shapes) and 15-25 % faster below 30 %, so auto means 2
+    // wherever it applies (tile <= 60 KB); 1 stays selectable for A/B runs.
+    const bool want2 = c->flat_mode == 2 || c->flat_mode == 0;
+    const bool flat2 = want2 && c->tile_bytes <= FLAT_MAX_TILE;
+    // Packing of the staged tile: bytes unless GM2_CFG_PACKING asked for two bits.  (Measured and dropped: staging the
+    // two-bit copy automatically for low-retention launches — from a two-bit tile a stored vector is two 1-wavefront
+    // LDS.32 instead of two 4-wavefront LDS.128, which relieves the L1 data pipe, but the expansion in registers costs
+    // more than that returns: 0.745 vs 0.811 of peak at 10 % gene retention, profiles/r02_sweep_two_bit_tile_rejected.log.)
     const bool two_bit = c->packing == 2;
     p.seq = two_bit ? c->d_seq2 : c->d_seq; p.tile_smem_bytes = two_bit ? c->tile_bytes / 4 : c->tile_bytes;
     p.tile_slot = c->d_tile_slot; p.slot_src = c->d_slot_src; p.slot_len = c->d_slot_len;
@@ -848,7 +858,6 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
         return 32 + (size_t)p.tile_smem_bytes + 64 + (size_t)p.slot_cap * 8 + (size_t)warps * (rt + 2) * 24;
     };
     const size_t dense_limit = 56 * 1024;
-    poll_kept_frac(c);
     int rt_cap = c->rt_cap;
     // Launch form, re-measured with the bitmap-indexed short-run form and the gene-density tile
     // (profiles/r02_emit_low_retention.md): with tiles of 28-48 KB the 72-register build is the faster one at
@@ -863,11 +872,6 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     // event table with 2 * rt_cap + 2 entries each, the rest (2 * rt_cap + 8 words) holds rt_cap + 4 bitmap entries
     // {event word, skip word}, one per 512-byte output row; phase I reads pairs of entries one pair ahead, so
     // the last five stay spare.
-    // Short-run form: the bitmap-indexed whole-visit form (2) is at least as fast as the per-batch cursor form (1)
-    // at every retention measured (0.1 ... 0.9, both genome shapes) and 15-25 % faster below 30 %, so auto means 2
-    // wherever it applies (one byte per base, tile <= 60 KB); 1 stays selectable for A/B runs.
-    const bool want2 = c->flat_mode == 2 || c->flat_mode == 0;
-    const bool flat2 = want2 && !two_bit && c->tile_bytes <= FLAT_MAX_TILE;
     p.flat_cap = flat2 ? 2 * rt_cap : 0;
     p.flat_bm_words = flat2 ? rt_cap - 1 : 0;
     const size_t sm = smem_for(rt_cap);
@@ -876,7 +880,9 @@ static int launch_emit(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* dev_out) {
     c->last_emit_ctas = dense ? 4 : 3;
     c->last_flat_mode = flat2 ? 2 : 1;
     void (*kern)(const EmitParams);
-    if (two_bit)
+    if (two_bit && flat2)
+        kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 2, 2> : k_emit<1, 3, 2, 2>) : (dense ? k_emit<0, 4, 2, 2> : k_emit<0, 3, 2, 2>);
+    else if (two_bit)
         kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 2, 1> : k_emit<1, 3, 2, 1>) : (dense ? k_emit<0, 4, 2, 1> : k_emit<0, 3, 2, 1>);
     else if (flat2)
         kern = c->store_policy == 1 ? (dense ? k_emit<1, 4, 1, 2> : k_emit<1, 3, 1, 2>) : (dense ? k_emit<0, 4, 1, 2> : k_emit<0, 3, 1, 2>);

@@ -476,7 +476,31 @@ __device__ __forceinline__ uint4 merge16(const uint4& x, const uint4& y, int k) 
 
 #define FLAT_MAX_TILE 61440          // R and S must fit 16 bits
 
-template <int POLICY>
+// The 16 output bytes whose first one is base `off` of the staged tile (off may be negative by < 16, or run past the
+// tile: both land in the pads or in this CTA's other shared memory and are never stored).  PACK 1: bytes, an unaligned
+// 16-byte window (two LDS.128 + word select + funnel shift).  PACK 2: two bits per base — the 32 bits holding the 16
+// codes are a funnel shift of two CONSECUTIVE words, and the lanes of a run read consecutive words: one wavefront
+// per load instead of four, which is what the L1 data pipe is short of at low retention; the price is the
+// expansion (spread + PRMT), ~5 more instructions per vector.
+template <int PACK>
+__device__ __forceinline__ uint4 tile_window16(uint32_t tile_a, int off) {
+    if (PACK == 2) {
+        const uint32_t wa = tile_a + (uint32_t)((off >> 4) << 2);
+        return expand16(__funnelshift_r(lds32(wa), lds32(wa + 4u), 2 * (off & 15)));
+    }
+    return lds_unaligned16(tile_a + (uint32_t)off);
+}
+template <int PACK>
+__device__ __forceinline__ uint4 tile_window16_part(uint32_t tile_a, int off, int b0, int b1) {
+    if (PACK == 2) return tile_window16<2>(tile_a, off);
+    return lds_unaligned16_part(tile_a + (uint32_t)off, b0, b1);
+}
+template <int PACK>
+__device__ __forceinline__ uint32_t tile_base_at(uint32_t tile_a, int off) {
+    return PACK == 2 ? base_at_2bit(tile_a, off) : lds8(tile_a + (uint32_t)off);
+}
+
+template <int POLICY, int PACK>
 __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32_t ev_a, uint32_t bm_a,
                                            uint32_t len_a, uint32_t src_a, uint32_t words, int nwords,
                                            uint8_t* __restrict__ out0 /* first output byte of the visit */,
@@ -578,11 +602,11 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
                     const uint32_t sa = has_prev ? xm : x, sb = has_prev ? x : x1, sc = has_prev ? x1 : x2;
                     const int kb = (int)(sb & 0xffffu) - p0;                      // bytes [0, kb) from source a, [kb, kc) from b
                     const int kc = nsrc == 3 ? (int)(sc & 0xffffu) - p0 : 16;     // ... and [kc, 16) from c
-                    const uint4 X = lds_unaligned16_part(tile_a + (sa >> 16) + (uint32_t)(p0 - (int)(sa & 0xffffu)), 0, kb);
-                    const uint4 Y = lds_unaligned16_part(tile_a + (sb >> 16) + (uint32_t)(p0 - (int)(sb & 0xffffu)), kb, kc);
+                    const uint4 X = tile_window16_part<PACK>(tile_a, (int)(sa >> 16) + p0 - (int)(sa & 0xffffu), 0, kb);
+                    const uint4 Y = tile_window16_part<PACK>(tile_a, (int)(sb >> 16) + p0 - (int)(sb & 0xffffu), kb, kc);
                     ov = merge16(X, Y, kb);
                     if (nsrc == 3) {
-                        const uint4 Z = lds_unaligned16_part(tile_a + (sc >> 16) + (uint32_t)(p0 - (int)(sc & 0xffffu)), kc, 16);
+                        const uint4 Z = tile_window16_part<PACK>(tile_a, (int)(sc >> 16) + p0 - (int)(sc & 0xffffu), kc, 16);
                         ov = merge16(ov, Z, kc);
                     }
                 } else {                                                          // many tiny runs in one vector
@@ -593,7 +617,7 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         while (p0 + j >= rn) { ++rc; xc = tb_load(a_a + 4u * rc); rn = (int)(tb_load(a_a + 4u * (rc + 1)) & 0xffffu); }
-                        w[j >> 2] |= lds8(tile_a + (xc >> 16) + (uint32_t)(p0 + j - (int)(xc & 0xffffu))) << (8 * (j & 3));
+                        w[j >> 2] |= tile_base_at<PACK>(tile_a, (int)(xc >> 16) + p0 + j - (int)(xc & 0xffffu)) << (8 * (j & 3));
                     }
                     ov = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -601,7 +625,8 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
             }
             if (last) tb_or(bm_a + 8u * (uint32_t)(v >> 5), 1u << (v & 31));
             if (R & 15) tb_or(bm_a + 8u * (uint32_t)(v >> 5) + 4u, 1u << (v & 31));
-            x = tile_a + (x >> 16) - (uint32_t)R;                                 // source address of output byte 0 in run r's frame
+            x = (PACK == 1 ? tile_a : 0u) + (x >> 16) - (uint32_t)R;              // source of output byte 0 in run r's frame:
+                                                                                  // shared address (bytes) / base index (two-bit)
         }
         const uint32_t bal = __ballot_sync(FULL_MASK, last);
         if (last) tb_store(ev_a + 4u * (ne + __popc(bal & lt_mask)), x);
@@ -628,8 +653,8 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
             const uint32_t ea0 = tb_load(evp + 4u * (uint32_t)__popc(mk.x & le_mask));
             const uint32_t ea1 = tb_load(evp + 4u * (uint32_t)(n0 + __popc(mk.z & le_mask)));
             evp += 4u * (uint32_t)(n0 + __popc(mk.z));
-            const uint4 v0 = lds_unaligned16(ea0 + pa);
-            const uint4 v1 = lds_unaligned16(ea1 + pa + 512u);
+            const uint4 v0 = PACK == 1 ? lds_unaligned16(ea0 + pa) : tile_window16<2>(tile_a, (int)(ea0 + pa));
+            const uint4 v1 = PACK == 1 ? lds_unaligned16(ea1 + pa + 512u) : tile_window16<2>(tile_a, (int)(ea1 + pa + 512u));
             if ((mk.y & lane_bit) == 0u) st128<POLICY>(d, v0);
             if ((mk.w & lane_bit) == 0u) st128<POLICY>(d + 512, v1);
             pa += 1024u; d += 1024;
@@ -663,7 +688,7 @@ __device__ __forceinline__ void visit_flat(uint32_t tile_a, uint32_t a_a, uint32
                 int rc = nr - 1; xc = tb_load(a_a + 4u * rc);
                 while (pos < (int)(xc & 0xffffu)) { --rc; xc = tb_load(a_a + 4u * rc); }
             }
-            st8<POLICY>(base16 + pos, lds8(tile_a + (xc >> 16) + (uint32_t)(pos - (int)(xc & 0xffffu))));
+            st8<POLICY>(base16 + pos, tile_base_at<PACK>(tile_a, (int)(xc >> 16) + pos - (int)(xc & 0xffffu)));
         }
     }
     __syncwarp();
@@ -737,13 +762,13 @@ k_emit(const EmitParams p)
     // the sample's length (last tile only) and ALL kept-bit words of the tile in one coalesced load
     int64_t m_roff = 0; int m_toff = 0, m_tend = 0, m_hl = 0; uint32_t m_words = 0u;
     // the flat form needs the tile's slot tables in shared memory and all its kept-bit words in one register per lane
-    const bool flat_ok = FLAT == 2 && PACK == 1 && p.flat_cap > 0 && p.flat_run_bytes > 0 && slots_staged && nwords <= 32;
+    const bool flat_ok = FLAT == 2 && p.flat_cap > 0 && p.flat_run_bytes > 0 && slots_staged && nwords <= 32;
     auto load_meta = [&](int64_t s) {
         m_roff = __ldg(p.rec_off + s);
         m_hl = __ldg(p.hdr_len + s);
         if (have_tile) {
             m_toff = __ldg(p.tile_off + (size_t)s * p.ntiles + tile);
-            if (FLAT == 2 && PACK == 1)          // where this tile's output ends: the next tile's offset / the sample's length
+            if (FLAT == 2)                       // where this tile's output ends: the next tile's offset / the sample's length
                 m_tend = tile == p.ntiles - 1 ? (int)__ldg(p.lengths + s) : __ldg(p.tile_off + (size_t)s * p.ntiles + tile + 1);
             m_words = lane < nwords ? __ldg(p.segkept + (size_t)s * p.SW + (sl0 >> 5) + lane) : 0u;
         }
@@ -769,7 +794,7 @@ k_emit(const EmitParams p)
         }
         uint8_t* seqout = rec + hl;
         bool flat = false;
-        if (FLAT == 2 && PACK == 1 && flat_ok) {
+        if (FLAT == 2 && flat_ok) {
             // runs of the visit = run starts in its kept-bit words (lane c holds word c); bytes = tend - toff
             uint32_t pm = __shfl_up_sync(FULL_MASK, words >> 31, 1);
             if (lane == 0) pm = 0u;
@@ -777,7 +802,7 @@ k_emit(const EmitParams p)
             const int bytes = tend - toff;
             flat = nrt > 0 && nrt <= p.flat_cap && bytes < nrt * p.flat_run_bytes && ((bytes + 14) >> 9) + 1 <= p.flat_bm_words;
             if (flat)
-                visit_flat<POLICY>(tile_a, rt_a, rt_a + 4u * (uint32_t)(p.flat_cap + 2), rt_a + 8u * (uint32_t)(p.flat_cap + 2),
+                visit_flat<POLICY, PACK>(tile_a, rt_a, rt_a + 4u * (uint32_t)(p.flat_cap + 2), rt_a + 8u * (uint32_t)(p.flat_cap + 2),
                                    len_a, src_a, words, nwords, seqout + toff, bytes, lane);
         }
         if (have_tile && !flat) {
