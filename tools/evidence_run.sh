@@ -8,7 +8,7 @@ O=gpurun_out/ev2
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu.log
 timeout 900 python bench.py --steps 20 --warmup 3 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2>&1; echo "reference rc=$?"
-LIGHT="--no-e2e --no-cpu-baseline --no-dropin --no-sharded --no-sweep"
+LIGHT="--no-e2e --no-cpu-baseline --no-dropin --no-sharded --no-sweep --no-c5"
 CMD="python bench.py --steps 2 --warmup 3 $LIGHT"
 $CMD > $O/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv $CMD > $O/ncu_list.log 2>&1; echo "ncu list rc=$?"
 # kernels before the timed region: 2 sizing plans x 3 + 4 warm-up steps x 4 + 3 solo passes x 4 = 34
