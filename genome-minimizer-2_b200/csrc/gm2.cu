@@ -530,6 +530,7 @@ GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx,
     if (!c->have_ref) return fail(c, GM2_ERR_STATE, "gm2_set_name_map: call gm2_set_reference first");
     if (V < 0 || !off) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: bad arguments");
     if (off[0] != 0) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: off[0] must be 0");
+    if (c->F >= K1_SINGLE) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: more than 2^30 genes");
     for (int32_t i = 0; i < V; ++i) if (off[i + 1] < off[i]) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: offsets must be non-decreasing");
     const int32_t n = off[V];
     if (n > 0 && !idx) return fail(c, GM2_ERR_INVALID, "gm2_set_name_map: idx is NULL");
@@ -549,13 +550,15 @@ GM2_API int gm2_set_name_map(gm2_ctx* c, const int32_t* off, const int32_t* idx,
         }
     }
     int rc;
-    if ((rc = dev_upload(c, &c->d_first_gene, first))) return rc;
-    if ((rc = dev_upload(c, &c->d_next_same, next))) return rc;
     {
         std::vector<uint32_t> hg(((size_t)V + 31) / 32 + 1, 0u);
         for (int32_t id = 0; id < V; ++id) if (first[id] >= 0) hg[(size_t)id >> 5] |= 1u << (id & 31);
         if ((rc = dev_upload(c, &c->d_has_gene, hg))) return rc;
     }
+    // names borne by exactly one gene (all but a handful) are flagged: the keep builders then never read next_same[]
+    for (int32_t id = 0; id < V; ++id) if (first[id] >= 0 && next[first[id]] < 0) first[id] |= K1_SINGLE;
+    if ((rc = dev_upload(c, &c->d_first_gene, first))) return rc;
+    if ((rc = dev_upload(c, &c->d_next_same, next))) return rc;
     c->V = V;
     if (c->d_forced_ids) { cudaFree(c->d_forced_ids); c->d_forced_ids = nullptr; }
     if (c->d_force_keep) { cudaFree(c->d_force_keep); c->d_force_keep = nullptr; }
@@ -694,11 +697,11 @@ GM2_API int gm2_plan_async(gm2_ctx* c, int64_t first_idx) {
         if ((rc = dev_reserve(c, &c->own_keep, &c->own_keep_cap, S * c->FW))) return rc;
         keep = c->own_keep;
         if (S > 0 && c->FW > 0) {
-            const size_t sm = (size_t)c->FW * 4;
-            if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: too many genes for the keep-row staging buffer");
+            const size_t sm = ((size_t)c->FW + (size_t)(c->V + 31) / 32) * 4;
+            if (sm > 200 * 1024) return fail(c, GM2_ERR_INVALID, "gm2_plan: too many genes / name ids for the keep builder's shared memory");
             if (sm > 48 * 1024) CU(c, cudaFuncSetAttribute(k_keep_from_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_keep_from_ids<<<(unsigned)S, K1_THREADS, sm, c->stream>>>(c->ids, c->ids_off, S, c->V, c->d_first_gene,
-                                                                        c->d_next_same, c->FW, c->own_keep);
+                                                                        c->d_next_same, c->d_has_gene, c->FW, c->own_keep);
             LAUNCH_CHECK(c, "k_keep_from_ids");
         }
     }

@@ -13,20 +13,37 @@
 //   sample with the table staged in shared memory measured 3x slower: with ~2 samples per
 //   resident warp the kernel ran for three whole sample latencies.)
 // ------------------------------------------------------------------------------------------
+//   Two things keep the per-id work short: a V-bit "names a gene" bitmap staged in shared memory filters the ids that
+//   match nothing (half of a real list: names of genes the reference does not carry) before any table access, and
+//   first_gene[] carries a flag for names borne by exactly one gene (all but a handful), so that the common id costs
+//   one table load and one shared-memory atomic and never touches next_same[].
 #define K1_THREADS 256
+#define K1_SINGLE 0x40000000            // first_gene[id] | K1_SINGLE: the name has exactly one gene
+__device__ __forceinline__ void k1_mark(uint32_t* row, const int32_t* __restrict__ first_gene,
+                                        const int32_t* __restrict__ next_same, int64_t id) {
+    const int e = __ldg(first_gene + id);
+    if (e < 0) return;
+    int g = e & (K1_SINGLE - 1);
+    atomicOr(&row[g >> 5], 1u << (g & 31));
+    if (!(e & K1_SINGLE))
+        for (g = __ldg(next_same + g); g >= 0; g = __ldg(next_same + g)) atomicOr(&row[g >> 5], 1u << (g & 31));
+}
+
 __global__ void __launch_bounds__(K1_THREADS)
 k_keep_from_ids(const int32_t* __restrict__ ids, const int64_t* __restrict__ off, int64_t S, int32_t V,
                 const int32_t* __restrict__ first_gene, const int32_t* __restrict__ next_same,
-                int FW, uint32_t* __restrict__ keep)
+                const uint32_t* __restrict__ has_gene, int FW, uint32_t* __restrict__ keep)
 {
-    extern __shared__ uint32_t k1_row[];
+    extern __shared__ uint32_t k1_row[];                    // FW words of the row, then ceil(V/32) words of has_gene
+    uint32_t* hg = k1_row + FW;
+    const int VW = (V + 31) >> 5;
     const int64_t s = blockIdx.x;
     for (int i = threadIdx.x; i < FW; i += blockDim.x) k1_row[i] = 0u;
+    for (int i = threadIdx.x; i < VW; i += blockDim.x) hg[i] = __ldg(has_gene + i);
     __syncthreads();
     const int64_t b = off[s], e = off[s + 1];
     auto mark = [&](int32_t id) {
-        if ((uint32_t)id < (uint32_t)V)
-            for (int g = __ldg(first_gene + id); g >= 0; g = __ldg(next_same + g)) atomicOr(&k1_row[g >> 5], 1u << (g & 31));
+        if ((uint32_t)id < (uint32_t)V && ((hg[id >> 5] >> (id & 31)) & 1u)) k1_mark(k1_row, first_gene, next_same, id);
     };
     // head up to a 16-byte boundary, 128-bit body, scalar tail
     const int64_t b4 = min((b + 3) & ~(int64_t)3, e), e4 = b4 + ((e - b4) & ~(int64_t)3);
@@ -82,9 +99,7 @@ k_keep_from_probs(const float* __restrict__ probs, int64_t S, int64_t V, int64_t
     __syncthreads();
     const float* p = probs + s * ld;
     int cnt = 0;
-    auto mark = [&](int64_t c) {
-        for (int g = __ldg(first_gene + c); g >= 0; g = __ldg(next_same + g)) atomicOr(&kp_row[g >> 5], 1u << (g & 31));
-    };
+    auto mark = [&](int64_t c) { k1_mark(kp_row, first_gene, next_same, c); };
     auto visit1 = [&](int64_t c, float v) {
         const uint32_t bit = 1u << (c & 31);
         if (v > thr) { ++cnt; if (hg[c >> 5] & bit) mark(c); }
