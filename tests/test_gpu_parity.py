@@ -353,10 +353,11 @@ def test_short_run_visits_match_the_oracle(mode):
         keep = rng.random((S, F)) < np.linspace(0.0, 0.6, S)[:, None]
         rows = synth.pack_keep_rows(keep)
         exp_len, _, exp_img = _oracle_image(seq, starts, ends, rows, first_idx=7)
-        for occ, frb in ((4, 640), (3, 1 << 20), (0, 200)):
+        for occ, frb, pack in ((4, 640, 1), (3, 1 << 20, 1), (0, 200, 1)) + (((3, 1 << 20, 2), (4, 640, 2)) if mode == 2 else ()):
             with _native.Context(0) as ctx:
                 if tile:
                     ctx.configure(_native.CFG_TILE_BYTES, tile)
+                ctx.configure(_native.CFG_PACKING, pack)          # 2: the whole-visit form from the two-bit staged tile
                 ctx.configure(_native.CFG_FLAT_MODE, mode)
                 ctx.configure(_native.CFG_EMIT_OCCUPANCY, occ)
                 ctx.configure(_native.CFG_FLAT_RUN_BYTES, frb)
@@ -364,7 +365,7 @@ def test_short_run_visits_match_the_oracle(mode):
                 ctx.load_keep_host(rows)
                 ctx.plan(7)
                 assert np.array_equal(ctx.lengths(), exp_len)
-                assert np.array_equal(_gpu_image(ctx, S), exp_img), (G, F, tile, occ, frb)
+                assert np.array_equal(_gpu_image(ctx, S), exp_img), (G, F, tile, occ, frb, pack)
 
 
 def test_many_genes_cover_one_segment():
@@ -546,8 +547,8 @@ def test_two_bit_packing_is_byte_identical_and_rejects_iupac():
 def test_fuzz_kernel_configurations():
     """Random genomes x random kernel configurations (tile size, warps, run-table size, packing,
     store policy, CTA order, batch) against the C oracle, byte for byte."""
-    rng = np.random.default_rng(20261018)
-    for trial in range(48):
+    rng = np.random.default_rng(int(os.environ.get("GM2_FUZZ_SEED", "20261018")))
+    for trial in range(int(os.environ.get("GM2_FUZZ_TRIALS", "48"))):          # soak runs: GM2_FUZZ_TRIALS=1000
         G = int(rng.choice([1, 31, 32, 33, 4095, 4096, 4097, int(rng.integers(5_000, 140_000))]))
         F = int(rng.integers(0, 400)) if G > 100 else int(rng.integers(0, 4))
         seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G)]
