@@ -1054,9 +1054,13 @@ GM2_API int gm2_emit_host(gm2_ctx* c, int64_t s0, int64_t s1, uint8_t* host_out,
     const int host_threads = c->host_threads > 0 ? c->host_threads : gm2host::default_threads();
     if (total > 0 && (c->wire == 2 || (c->wire == 0 && c->acgt_only && host_threads >= (gm2host::local_ranks() > 1 ? 4 : 6)))) {
         c->last_wire = 2;
-        // small pieces by default: the copy of piece i+1 hides under the expansion of piece i, and a caller that
-        // asks for one 256 MB range at a time (engine.drain) pays a short pipeline fill per call
-        return emit_host_packed(c, s0, s1, host_out, default_chunk ? env_i64("GM2_WIRE_CHUNK_BYTES", (int64_t)16 << 20) : chunk_bytes);
+        // Chunk size of the pipeline: 16 MB of image per chunk (GM2_WIRE_CHUNK_BYTES).  The copy of chunk i+1 hides
+        // under the expansion of chunk i; a caller that asks for one 256 MB range at a time (engine.drain) pays a short
+        // pipeline fill per call.  Bigger chunks mean fewer hand-overs but a staging ring (3 x chunk / 4) that no longer
+        // stays in the last-level cache: measured, 64 MB chunks are 10 % faster than 16 MB ones on this pool's 24-core
+        // hosts and 7 % slower (file outputs 30 % slower) on its 16-core hosts (profiles/r02_host_path.md).
+        const int64_t wire_chunk = default_chunk ? env_i64("GM2_WIRE_CHUNK_BYTES", (int64_t)16 << 20) : chunk_bytes;
+        return emit_host_packed(c, s0, s1, host_out, wire_chunk);
     }
     c->last_d2h_bytes = total;
     // staging must hold the largest single record of the range
