@@ -15,7 +15,9 @@
 //   one ballot per 32 slots and sample, kept lengths accumulated in registers and reduced once per
 //   tile (REDUX); warp k then scans the tile sums of sample k.
 // ------------------------------------------------------------------------------------------
+#ifndef PLAN_NS
 #define PLAN_NS 4
+#endif
 __device__ __forceinline__ bool keep_bit(const uint32_t* row, int g) {
     return g < 0 ? true : ((row[g >> 5] >> (g & 31)) & 1u) != 0u;
 }
