@@ -1013,23 +1013,36 @@ def main():
         except Exception:
             pass
 
+    def side_leg(name, fn):
+        """The legs beside the headline step.  A parity failure inside one aborts the run (SystemExit); any other
+        failure (a full tmpfs, an allocation on a busy box) is recorded in the leg's place instead of costing the
+        whole line — on one GPU only: with several ranks a leg's collectives need every rank, so errors propagate."""
+        if world > 1:
+            return fn()
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench.py: leg '{name}' failed: {e!r}\n")
+            torch.cuda.synchronize(dev)
+            return {"error": repr(e)[:400]}
+
     sweep = None
     if world == 1 and not args.no_sweep and args.genome == "k12" and not args.emit_debug:
-        sweep = retention_sweep(ctx, g, make_ctx, torch, dev, stream, peak)
+        sweep = side_leg("retention_sweep", lambda: retention_sweep(ctx, g, make_ctx, torch, dev, stream, peak))
         ctx.set_name_map(table.id2gene_off, table.id2gene_idx)
 
     sharded = None
     if not args.no_sharded and args.genome == "k12" and not args.emit_debug:
         job3 = Job(table, args.job_samples, args.retention, args.noise_ids, seed=3)
         sharded = {"job": f"C3: {args.job_samples} samples, K-12-shaped genome, gene retention {args.retention}, cut over {world} rank(s)",
-                   "device": sharded_device_leg(pair, g, job3, torch, dist, dev, stream, rank, world, barrier, S)}
-        sharded["file"] = sharded_file_leg(g, table, job3, rank, world, barrier, args.file_gb_per_rank)
+                   "device": side_leg("sharded.device", lambda: sharded_device_leg(pair, g, job3, torch, dist, dev, stream, rank, world, barrier, S))}
+        sharded["file"] = side_leg("sharded.file", lambda: sharded_file_leg(g, table, job3, rank, world, barrier, args.file_gb_per_rank))
     config5 = None
     if not args.no_c5 and args.genome == "k12" and not args.emit_debug:
-        config5 = config5_leg(g, table, torch, dist, dev, local_rank, rank, world, barrier)
+        config5 = side_leg("config5", lambda: config5_leg(g, table, torch, dist, dev, local_rank, rank, world, barrier))
     dropin = None
     if not args.no_dropin and args.genome == "k12":
-        dropin = dropin_entry(g, table, rank, world, barrier)
+        dropin = side_leg("dropin_c1", lambda: dropin_entry(g, table, rank, world, barrier))
         if sharded is not None:
             sharded["entry"] = dropin
 
