@@ -410,7 +410,10 @@ class ContextPair:
         order; ring: two (dev_ptr, capacity) output buffers, chunk i is emitted into ring[i & 1].
         `after_emit(i, ctx)` may issue the chunk's consumer on ctx's stream (hashing, a copy, ...): ring[i & 1] is
         not overwritten before that work has finished.  Returns the number of chunks issued; call sync() on both
-        contexts (or order a stream after them) before reading results on the host."""
+        contexts (or order a stream after them) before reading results on the host.  Nothing here waits for a
+        plan, so the capacity of a ring buffer cannot be checked against the chunk's image size (gm2_emit_dev
+        checks it only when the plan is already on the host): size the ring from a planning pass, as
+        bench.py's sharded leg does, or for the worst case (every base of every sample kept)."""
         a, b = self.ctx
         b.order_after(a)
         n = 0
