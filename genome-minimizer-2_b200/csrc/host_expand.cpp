@@ -168,9 +168,13 @@ static int write_header(uint8_t* dst, const char* prefix, int prefix_len, unsign
     return prefix_len + nd + 1;
 }
 
-// One task = a sixteenth of one sample's tiles (finer than a sample so that the tail of a chunk does not
-// leave threads idle); the first part also writes the header line, the last one the final newline.
-static const int TASKS_PER_SAMPLE = 16;
+// One task = 1/48 of one sample's tiles (a few tiles, ~55 KB of output): a 16 MB chunk is ~300 tasks for 16-32
+// threads, so the tail of a chunk leaves little idle time (measured: 16 tasks per sample 166.5 Gbp/s end to end,
+// 48 tasks 172.3 on the same host); the first part also writes the header line, the last one the final newline.
+#ifndef GM2_TASKS_PER_SAMPLE
+#define GM2_TASKS_PER_SAMPLE 48
+#endif
+static const int TASKS_PER_SAMPLE = GM2_TASKS_PER_SAMPLE;
 
 static void expand_task(const ChunkView& v, int64_t task) {
     const int64_t i = task / TASKS_PER_SAMPLE;
